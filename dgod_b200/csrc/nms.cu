@@ -1,0 +1,386 @@
+// Bitmask batched NMS.
+//
+// Reference behaviour restated (TV = torchvision 0.26.0):
+//   nms                 TV ops/boxes.py:20-48 -> torchvision::nms CPU kernel: stable descending
+//                       sort of the scores, greedy pass, suppress iff IoU > threshold with the
+//                       fp32 IoU widened to double for the comparison (SURVEY.md §8c probes)
+//   batched_nms         TV ops/boxes.py:51-120: coordinate-offset trick (<= 1000 boxes on CPU)
+//                       or per-group loop ("vanilla"), both honoured via `offset_mode`
+//
+// Pipeline (all segments = images and all groups = levels/classes in one set of launches):
+//   1. prepare   64-bit key = segment:16 | group:16 | ~ordered(score):32, value = input index
+//   2. sort      bitonic, ascending (key, index)  => processing order, runs = (segment, group)
+//   3. gather    boxes into processing order (+ the offset trick's fp32 shift), 32-bit run keys
+//   4. mask      64x64 IoU tiles from shared memory -> per-row 64-bit suppression words, only
+//                inside a run and above the diagonal (block-diagonal, upper-triangular)
+//   5. scan      one CTA per run: resolve 64 candidates per step from the diagonal word, OR the
+//                kept rows into the run's removed-bitmap in shared memory
+//   6. re-key kept entries as segment | ~score, sort again, write segment-relative indices in
+//      descending score order, truncated to max_out_per_seg
+//
+// Bytes: 28 B per box in and 8 B per kept box out are compulsory; the mask adds
+// 2 * 8 B * sum_runs n_r^2/128 (write + read).  The pair evaluations (sum_runs n_r^2/2, ~25
+// fp32 instructions each) are the real cost for large runs — see DESIGN.md for the roofline.
+#include "nms_core.cuh"
+#include "sort.cuh"
+
+namespace dgod {
+
+constexpr unsigned long long kKeyMax = ~0ull;
+
+// ---------------------------------------------------------------------------- mask
+__global__ void __launch_bounds__(256)
+nms_mask_kernel(const float4* __restrict__ sbox, const uint32_t* __restrict__ runkey, int n_pos,
+                float thr, unsigned long long* __restrict__ mask, int row_words) {
+  // column tile, transposed to [bit][chunk] with a one-slot pad: lanes (= chunks) read
+  // consecutive float4s, the staging stores hit distinct bank groups.
+  __shared__ float4 s_box[64][kMaskColSpan + 1];
+  __shared__ uint32_t s_key[64][kMaskColSpan + 1];
+  const int r = blockIdx.x;                                      // row chunk
+  const int cbase = (r / kMaskColSpan + blockIdx.y) * kMaskColSpan;  // first column chunk
+  const int row0 = r * 64;
+  const long long col0 = (long long)cbase * 64;
+  if (row0 >= n_pos || col0 >= n_pos) return;
+  const int last_row = min(row0 + 63, n_pos - 1);
+  // run keys are non-decreasing: if the first column is already past the last row's run,
+  // no pair of this tile shares a run.  Padding rows (kNoRun) never own pairs.
+  uint32_t rk_last = runkey[last_row];
+  if (rk_last == kNoRun) {
+    // find the last real row of the chunk (rare: only the chunk holding the tail)
+    int p = last_row;
+    while (p >= row0 && runkey[p] == kNoRun) --p;
+    if (p < row0) return;
+    rk_last = runkey[p];
+  }
+  if (runkey[col0] > rk_last) return;
+
+  for (int i = threadIdx.x; i < 64 * kMaskColSpan; i += blockDim.x) {
+    long long q = col0 + i;
+    int cc = i >> 6, b = i & 63;
+    float4 bx = make_float4(0, 0, 0, 0);
+    uint32_t k = kNoRun;
+    if (q < n_pos) { bx = sbox[q]; k = runkey[q]; }
+    s_box[b][cc] = bx;
+    s_key[b][cc] = k;
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = cbase + lane;  // this lane's column chunk
+#pragma unroll 1
+  for (int rr = warp; rr < 64; rr += 8) {
+    const int p = row0 + rr;
+    if (p >= n_pos) break;
+    const uint32_t rk = runkey[p];
+    if (rk == kNoRun) continue;
+    const int w = c - r;
+    if (w < 0 || w >= row_words) continue;
+    const float4 a = sbox[p];
+    const float area_a = box_area_exact(a.x, a.y, a.z, a.w);
+    unsigned long long bits = 0ull;
+    const long long qbase = (long long)c * 64;
+    if (qbase + 63 > p && s_key[0][lane] <= rk && s_key[63][lane] >= rk) {
+#pragma unroll 8
+      for (int b = 0; b < 64; ++b) {
+        if (s_key[b][lane] == rk && qbase + b > p) {
+          const float4 bb = s_box[b][lane];
+          float v = iou_exact(a, area_a, bb, box_area_exact(bb.x, bb.y, bb.z, bb.w));
+          if (v > thr) bits |= (1ull << b);
+        }
+      }
+    }
+    mask[(size_t)p * row_words + w] = bits;
+  }
+}
+
+int launch_nms_mask(const float4* sbox, const uint32_t* runkey, int n_pos, int max_run_len,
+                    float thr, unsigned long long* mask, cudaStream_t st) {
+  if (n_pos <= 0) return DGOD_OK;
+  const int row_words = nms_mask_row_words(max_run_len);
+  // column chunks reachable from a row chunk: [r, r + max_run_len/64 + 1]; the span containing
+  // r starts up to kMaskColSpan-1 chunks before r.
+  const int spans = (max_run_len / 64 + 1 + kMaskColSpan - 1) / kMaskColSpan + 1;
+  dim3 grid(cdiv(n_pos, 64), spans);
+  nms_mask_kernel<<<grid, 256, 0, st>>>(sbox, runkey, n_pos, thr, mask, row_words);
+  DGOD_LAUNCHED();
+  return DGOD_OK;
+}
+
+// ---------------------------------------------------------------------------- scan
+__global__ void __launch_bounds__(256)
+nms_scan_kernel(const unsigned long long* __restrict__ mask, int row_words,
+                const uint32_t* __restrict__ runkey, const uint8_t* __restrict__ alive, int n_pos,
+                unsigned long long* __restrict__ keepbits, int32_t* __restrict__ compact_pos,
+                int32_t* __restrict__ run_count) {
+  extern __shared__ unsigned long long s_removed[];  // row_words words
+  __shared__ unsigned long long s_diag[64];
+  __shared__ uint32_t s_ballot[2];
+  __shared__ unsigned long long s_kept;
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const int p0 = c * 64;
+  if (tid < 64) {
+    const int p = p0 + tid;
+    bool start = false;
+    if (p < n_pos) {
+      uint32_t k = runkey[p];
+      start = k != kNoRun && (p == 0 || runkey[p - 1] != k);
+    }
+    uint32_t bal = __ballot_sync(0xffffffffu, start);
+    if ((tid & 31) == 0) s_ballot[tid >> 5] = bal;
+  }
+  __syncthreads();
+  unsigned long long starts = ((unsigned long long)s_ballot[1] << 32) | s_ballot[0];
+  if (starts == 0ull) return;
+
+  while (starts) {
+    const int sb = __ffsll((long long)starts) - 1;
+    starts &= starts - 1;
+    const int s = p0 + sb;
+    const uint32_t rk = runkey[s];
+    int lo = s + 1, hi = n_pos;  // upper bound of rk in the non-decreasing key array
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (runkey[mid] <= rk) lo = mid + 1; else hi = mid;
+    }
+    const int e = lo;
+    const int cs = s >> 6, ce = (e - 1) >> 6;
+    __syncthreads();  // previous run done with s_removed
+    for (int w = tid; w <= ce - cs && w < row_words; w += blockDim.x) s_removed[w] = 0ull;
+    __syncthreads();
+    int count = 0;
+    for (int cc = cs; cc <= ce; ++cc) {
+      if (tid < 64) {
+        const int p = cc * 64 + tid;
+        bool in = p >= s && p < e && (!alive || alive[p]);
+        s_diag[tid] = in ? mask[(size_t)p * row_words] : 0ull;
+        uint32_t bal = __ballot_sync(0xffffffffu, in);
+        if ((tid & 31) == 0) s_ballot[tid >> 5] = bal;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        unsigned long long al = (((unsigned long long)s_ballot[1] << 32) | s_ballot[0]) & ~s_removed[cc - cs];
+        unsigned long long kept = 0ull;
+#pragma unroll 8
+        for (int b = 0; b < 64; ++b) {
+          if ((al >> b) & 1ull) {
+            kept |= (1ull << b);
+            al &= ~s_diag[b];
+          }
+        }
+        s_kept = kept;
+      }
+      __syncthreads();
+      const unsigned long long kept = s_kept;
+      for (int w = tid + 1; cc + w <= ce; w += blockDim.x) {
+        unsigned long long acc = 0ull, kk = kept;
+        while (kk) {
+          const int b = __ffsll((long long)kk) - 1;
+          kk &= kk - 1;
+          acc |= mask[(size_t)(cc * 64 + b) * row_words + w];
+        }
+        s_removed[cc - cs + w] |= acc;
+      }
+      if (tid < 64 && ((kept >> tid) & 1ull) && compact_pos) {
+        const int j = count + __popcll(kept & ((1ull << tid) - 1ull));
+        compact_pos[s + j] = cc * 64 + tid;
+      }
+      if (tid == 0 && kept) atomicOr(&keepbits[cc], kept);
+      count += __popcll(kept);
+      __syncthreads();
+    }
+    if (run_count && tid == 0) run_count[rk] = count;
+  }
+}
+
+int launch_nms_scan(const unsigned long long* mask, const uint32_t* runkey, const uint8_t* alive,
+                    int n_pos, int max_run_len, unsigned long long* keepbits,
+                    int32_t* compact_pos, int32_t* run_count, cudaStream_t st) {
+  if (n_pos <= 0) return DGOD_OK;
+  const int row_words = nms_mask_row_words(max_run_len);
+  const size_t smem = (size_t)row_words * sizeof(unsigned long long);
+  if (smem > 48 * 1024) {
+    DGOD_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+  }
+  nms_scan_kernel<<<cdiv(n_pos, 64), 256, smem, st>>>(mask, row_words, runkey, alive, n_pos,
+                                                     keepbits, compact_pos, run_count);
+  DGOD_LAUNCHED();
+  return DGOD_OK;
+}
+
+// ---------------------------------------------------------------------------- generic pipeline
+__device__ __forceinline__ int find_segment(const int32_t* __restrict__ seg_offsets, int n_seg, int p) {
+  int lo = 0, hi = n_seg;  // largest s with seg_offsets[s] <= p
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (seg_offsets[mid] <= p) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256)
+nms_prepare_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
+                   const int64_t* __restrict__ groups, const uint8_t* __restrict__ valid,
+                   const int32_t* __restrict__ seg_offsets, int n_seg, int n_total, int n_pow2,
+                   int offset_mode, unsigned long long* __restrict__ keys,
+                   uint32_t* __restrict__ vals, uint32_t* __restrict__ seg_max,
+                   int32_t* __restrict__ status) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pow2) return;
+  unsigned long long key = kKeyMax;
+  if (p < n_total && (!valid || valid[p])) {
+    const int seg = find_segment(seg_offsets, n_seg, p);
+    long long g = groups ? groups[p] : 0;
+    if (g < 0 || g > 65535) { atomicOr(status, 1); g = 0; }
+    if (offset_mode) {
+      float4 b = ld_box(boxes, p);
+      float m = fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w));  // boxes.max(), TV ops/boxes.py:99
+      atomicMax(&seg_max[seg], float_ordered(m));
+      g = 0;  // one run per segment; the groups act through the coordinate shift only
+    }
+    key = ((unsigned long long)seg << 48) | ((unsigned long long)g << 32) |
+          (unsigned long long)(~float_ordered(scores[p]));
+  }
+  keys[p] = key;
+  vals[p] = (uint32_t)p;
+}
+
+__global__ void __launch_bounds__(256)
+nms_gather_kernel(const float* __restrict__ boxes, const int64_t* __restrict__ groups,
+                  const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals,
+                  const uint32_t* __restrict__ seg_max, int n_pow2, int offset_mode,
+                  float4* __restrict__ sbox, uint32_t* __restrict__ runkey) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pow2) return;
+  const unsigned long long key = keys[p];
+  if (key == kKeyMax) { runkey[p] = kNoRun; return; }
+  const uint32_t idx = vals[p];
+  float4 b = ld_box(boxes, idx);
+  if (offset_mode) {
+    const int seg = (int)(key >> 48);
+    const float maxc = float_from_ordered(seg_max[seg]);
+    const float g = groups ? (float)groups[idx] : 0.f;           // idxs.to(boxes)
+    const float off = __fmul_rn(g, __fadd_rn(maxc, 1.f));        // TV ops/boxes.py:100
+    b.x = __fadd_rn(b.x, off); b.y = __fadd_rn(b.y, off);        // TV ops/boxes.py:101
+    b.z = __fadd_rn(b.z, off); b.w = __fadd_rn(b.w, off);
+  }
+  sbox[p] = b;
+  runkey[p] = (uint32_t)(key >> 32);
+}
+
+__global__ void __launch_bounds__(256)
+nms_rekey_kernel(unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ keepbits,
+                 int n_pow2) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pow2) return;
+  const bool kept = (keepbits[p >> 6] >> (p & 63)) & 1ull;
+  const unsigned long long key = keys[p];
+  keys[p] = (kept && key != kKeyMax) ? (key & ~(0xffffull << 32)) : kKeyMax;
+}
+
+__global__ void __launch_bounds__(256)
+nms_output_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals,
+                  const int32_t* __restrict__ seg_offsets, int n_pow2, int out_stride,
+                  int64_t* __restrict__ keep_out, int32_t* __restrict__ keep_count) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pow2) return;
+  const unsigned long long key = keys[p];
+  if (key == kKeyMax) return;
+  const int seg = (int)(key >> 48);
+  const unsigned long long first_key = (unsigned long long)seg << 48;
+  int lo = 0, hi = p;  // lower bound of first_key in keys[0..p]
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (keys[mid] < first_key) lo = mid + 1; else hi = mid;
+  }
+  const int rank = p - lo;
+  if (rank < out_stride)
+    keep_out[(size_t)seg * out_stride + rank] = (int64_t)vals[p] - seg_offsets[seg];
+  const unsigned long long next = (p + 1 < n_pow2) ? keys[p + 1] : kKeyMax;
+  if (next == kKeyMax || (int)(next >> 48) != seg) keep_count[seg] = min(rank + 1, out_stride);
+}
+
+struct NmsBuffers {
+  unsigned long long* keys;
+  uint32_t* vals;
+  float4* sbox;
+  uint32_t* runkey;
+  unsigned long long* mask;
+  unsigned long long* keepbits;
+  uint32_t* seg_max;
+};
+
+static size_t carve(Workspace& ws, NmsBuffers& b, int n_total, int n_seg, int max_seg_len) {
+  const int P = next_pow2(n_total > 0 ? n_total : 1);
+  b.keys = ws.take<unsigned long long>(P);
+  b.vals = ws.take<uint32_t>(P);
+  b.sbox = ws.take<float4>(P);
+  b.runkey = ws.take<uint32_t>(P);
+  b.keepbits = ws.take<unsigned long long>(P / 64 + 1);
+  b.seg_max = ws.take<uint32_t>(n_seg > 0 ? n_seg : 1);
+  b.mask = ws.take<unsigned long long>((size_t)(n_total > 0 ? n_total : 1) * nms_mask_row_words(max_seg_len));
+  return ws.used;
+}
+
+}  // namespace dgod
+
+using namespace dgod;
+
+extern "C" size_t dgod_nms_workspace_bytes(int n_total, int n_seg, int max_seg_len) {
+  Workspace ws(nullptr, 0);
+  NmsBuffers b;
+  return carve(ws, b, n_total, n_seg, max_seg_len);
+}
+
+extern "C" int dgod_nms_batched(const float* boxes, const float* scores, const int64_t* groups,
+                                const uint8_t* valid, const int32_t* seg_offsets, int n_seg,
+                                int n_total, int max_seg_len, double iou_threshold,
+                                int offset_mode, int max_out_per_seg, int64_t* keep_out,
+                                int32_t* keep_count, int32_t* status, void* workspace,
+                                size_t workspace_bytes, dgod_stream_t stream) {
+  DGOD_REQUIRE(n_seg >= 0 && n_total >= 0 && max_seg_len >= 0, "dgod_nms_batched: negative size");
+  DGOD_REQUIRE(n_seg < 65535, "dgod_nms_batched: at most 65534 segments per call");
+  DGOD_REQUIRE(max_seg_len <= n_total, "dgod_nms_batched: max_seg_len > n_total");
+  if (n_seg == 0) return DGOD_OK;
+  DGOD_REQUIRE(keep_count && status && seg_offsets, "dgod_nms_batched: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  DGOD_CUDA(cudaMemsetAsync(keep_count, 0, (size_t)n_seg * sizeof(int32_t), st));
+  DGOD_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+  if (n_total == 0) return DGOD_OK;
+  DGOD_REQUIRE(boxes && scores && keep_out, "dgod_nms_batched: null pointer");
+  Workspace ws(workspace, workspace_bytes);
+  NmsBuffers b;
+  carve(ws, b, n_total, n_seg, max_seg_len);
+  if (!workspace || !ws.ok()) {
+    set_error("dgod_nms_batched: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
+    return DGOD_ERR_WORKSPACE;
+  }
+  const int P = next_pow2(n_total);
+  const int out_stride = max_out_per_seg > 0 ? max_out_per_seg : max_seg_len;
+  const float thr = float_round_down(iou_threshold);
+  DGOD_CUDA(cudaMemsetAsync(b.keepbits, 0, (size_t)(P / 64 + 1) * sizeof(unsigned long long), st));
+  if (offset_mode) DGOD_CUDA(cudaMemsetAsync(b.seg_max, 0, (size_t)n_seg * sizeof(uint32_t), st));
+
+  nms_prepare_kernel<<<cdiv(P, 256), 256, 0, st>>>(boxes, scores, groups, valid, seg_offsets, n_seg,
+                                                   n_total, P, offset_mode, b.keys, b.vals,
+                                                   b.seg_max, status);
+  DGOD_LAUNCHED();
+  int rc = bitonic_sort(b.keys, b.vals, P, st);
+  if (rc) return rc;
+  nms_gather_kernel<<<cdiv(P, 256), 256, 0, st>>>(boxes, groups, b.keys, b.vals, b.seg_max, P,
+                                                  offset_mode, b.sbox, b.runkey);
+  DGOD_LAUNCHED();
+  // positions >= n_total are padding (kNoRun) and sort to the tail: only n_total positions matter
+  rc = launch_nms_mask(b.sbox, b.runkey, n_total, max_seg_len, thr, b.mask, st);
+  if (rc) return rc;
+  rc = launch_nms_scan(b.mask, b.runkey, nullptr, n_total, max_seg_len, b.keepbits, nullptr, nullptr, st);
+  if (rc) return rc;
+  nms_rekey_kernel<<<cdiv(P, 256), 256, 0, st>>>(b.keys, b.keepbits, P);
+  DGOD_LAUNCHED();
+  rc = bitonic_sort(b.keys, b.vals, P, st);
+  if (rc) return rc;
+  nms_output_kernel<<<cdiv(P, 256), 256, 0, st>>>(b.keys, b.vals, seg_offsets, P, out_stride,
+                                                  keep_out, keep_count);
+  DGOD_LAUNCHED();
+  return DGOD_OK;
+}

@@ -1,0 +1,29 @@
+// Core of the bitmask NMS shared by the generic batched op (nms.cu) and the RPN pipeline
+// (rpn.cu).  Both present their candidates in *processing order*: positions 0..n_pos-1 with a
+// non-decreasing 32-bit run key; a run (maximal range of equal keys) is one independent greedy
+// NMS problem whose members are already in descending score order.
+#pragma once
+#include "common.cuh"
+
+namespace dgod {
+
+constexpr uint32_t kNoRun = 0xffffffffu;  // run key of padding / masked-out positions
+constexpr int kMaskColSpan = 32;          // 64-column chunks handled per mask CTA
+
+// Words per mask row: a row covers column chunks [p/64, p/64 + words).
+static inline int nms_mask_row_words(int max_run_len) { return max_run_len / 64 + 2; }
+
+// mask[p*row_words + w] bit b  <=>  position q = (p/64 + w)*64 + b is in p's run, q > p, and
+// IoU(p,q) > threshold.
+int launch_nms_mask(const float4* sbox, const uint32_t* runkey, int n_pos, int max_run_len,
+                    float thr_rounded_down, unsigned long long* mask, cudaStream_t st);
+
+// Sequential greedy pass per run.  alive (optional, per position) = 0 removes a candidate
+// before NMS.  keepbits must be zeroed by the caller.  compact_pos (optional): kept positions
+// of a run written contiguously from the run's first position; run_count (optional) is indexed
+// by run key.
+int launch_nms_scan(const unsigned long long* mask, const uint32_t* runkey, const uint8_t* alive,
+                    int n_pos, int max_run_len, unsigned long long* keepbits,
+                    int32_t* compact_pos, int32_t* run_count, cudaStream_t st);
+
+}  // namespace dgod

@@ -1,0 +1,406 @@
+// RPN proposal stage: per-level top-k on the raw objectness maps, analytic anchors, decode of
+// the survivors only, clip / small-box / score filters, per-level NMS, score-ordered merge.
+// 
+//
+// Reference behaviour restated (TV = torchvision 0.26.0; called from fasterrcnn.py:166-182):
+//   anchors            TV models/detection/anchor_utils.py:58-74,84-133
+//   permute/concat     TV models/detection/rpn.py:81-110  -> candidate order (level, y, x, a)
+//   decode             TV models/detection/_utils.py:186-224 (weights 1,1,1,1; clamp log(1000/16))
+//   per-level top-k    TV models/detection/rpn.py:231-240,263-272
+//   filters + NMS      TV models/detection/rpn.py:276-297 (clip, remove_small 1e-3, score >= 0,
+//                      batched_nms per level, keep[:post_nms_top_n])
+//
+// The reference decodes all A anchors per image (A = 155k..268k) and materialises anchors,
+// permuted logits and permuted deltas; here a candidate is touched only if it survives the
+// per-level top-k, so the compulsory traffic is 4 B per anchor (objectness) + 16 B per survivor.
+// Where torch.topk leaves the order of *equal logits* implementation-defined, this kernel uses
+// ascending anchor index ("ties").
+#include "nms_core.cuh"
+
+namespace dgod {
+
+constexpr int kTopkThreads = 1024;
+
+struct RpnDev {
+  const float* obj[DGOD_MAX_LEVELS];
+  const float* del[DGOD_MAX_LEVELS];
+  int n_levels, A, n_img, k_tot, flat;
+  int H[DGOD_MAX_LEVELS], W[DGOD_MAX_LEVELS], sh[DGOD_MAX_LEVELS], sw[DGOD_MAX_LEVELS];
+  int n_l[DGOD_MAX_LEVELS];     // anchors per level
+  int a_off[DGOD_MAX_LEVELS];   // anchor offset of the level inside an image (flat layout)
+  int k_l[DGOD_MAX_LEVELS];     // min(pre_nms_top_n, n_l)
+  int c_off[DGOD_MAX_LEVELS];   // candidate offset of the level inside an image
+  int a_total;
+  float min_size, score_thresh, xform_clip;
+  float cell[DGOD_MAX_LEVELS][DGOD_MAX_CELL_ANCHORS][4];
+};
+
+// ---- CTA-wide radix select: threshold of the k smallest 32-bit keys --------------------------
+// keyfn(m, key) -> bool participates.  On return (all threads): T = k-th smallest key,
+// n_lt = #keys < T, n_eq = #keys == T.  s_hist: 256 words, s_bc: 4 words of shared scratch.
+template <typename KeyFn>
+__device__ void radix_select(KeyFn keyfn, int n, int k, uint32_t* s_hist, uint32_t* s_bc,
+                             uint32_t& T, int& n_lt, int& n_eq) {
+  uint32_t prefix = 0u, pmask = 0u;
+  int remaining = k, lt_total = 0, eq = 0;
+  const int lane = threadIdx.x & 31;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0u;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+      const int m = base + threadIdx.x;
+      uint32_t key = 0u;
+      bool part = m < n && keyfn(m, key) && ((key & pmask) == prefix);
+      const uint32_t digit = part ? ((key >> shift) & 255u) : 256u;
+      const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+      if (part && lane == __ffs(peers) - 1) atomicAdd(&s_hist[digit], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t loc[8], sum = 0u;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { loc[i] = s_hist[lane * 8 + i]; sum += loc[i]; }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      const uint32_t excl = incl - sum;
+      const uint32_t hit = __ballot_sync(0xffffffffu, incl >= (uint32_t)remaining);
+      if (lane == __ffs(hit) - 1) {
+        uint32_t cum = excl;
+        int d = 0;
+        for (; d < 8; ++d) {
+          if (cum + loc[d] >= (uint32_t)remaining) break;
+          cum += loc[d];
+        }
+        s_bc[0] = (uint32_t)(lane * 8 + d);
+        s_bc[1] = cum;        // keys below the chosen digit within the current prefix
+        s_bc[2] = loc[d];
+      }
+    }
+    __syncthreads();
+    const uint32_t digit = s_bc[0];
+    lt_total += (int)s_bc[1];
+    remaining -= (int)s_bc[1];
+    eq = (int)s_bc[2];
+    prefix |= digit << shift;
+    pmask |= 255u << shift;
+    __syncthreads();
+  }
+  T = prefix; n_lt = lt_total; n_eq = eq;
+}
+
+__device__ __forceinline__ void append_selected(bool sel, unsigned long long rec,
+                                                unsigned long long* s_sel, int* s_count) {
+  const uint32_t bal = __ballot_sync(0xffffffffu, sel);
+  if (bal == 0u) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == __ffs(bal) - 1) base = atomicAdd(s_count, __popc(bal));
+  base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+  if (sel) s_sel[base + __popc(bal & ((1u << lane) - 1u))] = rec;
+}
+
+__device__ __forceinline__ float sigmoid_rn(float x) {
+  // correctly rounded (up to double error) sigmoid; torch's CPU sigmoid is within 1 ulp of it
+  return (float)(1.0 / (1.0 + exp(-(double)x)));
+}
+
+// One CTA per (level, image): top-k of the level's objectness, sorted, decoded, filtered.
+__global__ void __launch_bounds__(kTopkThreads)
+rpn_topk_decode_kernel(const RpnDev g, const float* __restrict__ proposals_flat,
+                       const float* __restrict__ objectness_flat,
+                       const float* __restrict__ image_sizes, float4* __restrict__ sbox,
+                       float* __restrict__ cscore, uint8_t* __restrict__ alive,
+                       uint32_t* __restrict__ runkey) {
+  extern __shared__ unsigned long long s_sel[];  // next_pow2(k) records: ~ordered(logit):32 | r:32
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_bc[4];
+  __shared__ int s_count;
+  const int l = blockIdx.x, b = blockIdx.y;
+  const int n = g.n_l[l], k = g.k_l[l], A = g.A;
+  const int HW = g.H[l] * g.W[l];
+  const float* __restrict__ obj =
+      g.flat ? objectness_flat + (size_t)b * g.a_total + g.a_off[l] : g.obj[l] + (size_t)b * n;
+  // memory index m -> reference index r (position in torchvision's (y, x, a) flattening)
+  auto ref_index = [&](int m) -> uint32_t {
+    if (g.flat) return (uint32_t)m;
+    const int a = m / HW, rem = m - a * HW;
+    return (uint32_t)(rem * A + a);
+  };
+  auto key_logit = [&](int m, uint32_t& key) -> bool {
+    key = ~float_ordered(__ldg(obj + m) + 0.f);  // smallest key = largest logit
+    return true;
+  };
+  int kp = 1;
+  while (kp < k) kp <<= 1;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+
+  if (n <= k) {
+    for (int base = 0; base < n; base += blockDim.x) {
+      const int m = base + threadIdx.x;
+      uint32_t key = 0u;
+      const bool sel = m < n && key_logit(m, key);
+      append_selected(sel, ((unsigned long long)key << 32) | ref_index(m < n ? m : 0), s_sel, &s_count);
+    }
+  } else {
+    uint32_t T; int n_lt, n_eq;
+    radix_select(key_logit, n, k, s_hist, s_bc, T, n_lt, n_eq);
+    const int need = k - n_lt;  // how many of the n_eq logits equal to the threshold are taken
+    uint32_t T2 = 0xffffffffu;
+    if (need < n_eq) {
+      // more ties than slots: take those with the smallest reference index
+      auto key_tie = [&](int m, uint32_t& key2) -> bool {
+        uint32_t k1; key_logit(m, k1);
+        key2 = ref_index(m);
+        return k1 == T;
+      };
+      int a_, b_;
+      radix_select(key_tie, n, need, s_hist, s_bc, T2, a_, b_);
+    }
+    for (int base = 0; base < n; base += blockDim.x) {
+      const int m = base + threadIdx.x;
+      uint32_t key = 0u, r = 0u;
+      bool sel = false;
+      if (m < n) {
+        key_logit(m, key);
+        r = ref_index(m);
+        sel = key < T || (key == T && r <= T2);
+      }
+      append_selected(sel, ((unsigned long long)key << 32) | r, s_sel, &s_count);
+    }
+  }
+  __syncthreads();
+  for (int i = k + threadIdx.x; i < kp; i += blockDim.x) s_sel[i] = ~0ull;
+  __syncthreads();
+  // bitonic sort of the kp records, ascending: logit descending, ties by reference index
+  for (int kk = 2; kk <= kp; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int q = threadIdx.x; q < (kp >> 1); q += blockDim.x) {
+        const int i = 2 * q - (q & (j - 1)), o = i + j;
+        const bool asc = (i & kk) == 0;
+        const unsigned long long x = s_sel[i], y = s_sel[o];
+        if ((x > y) == asc) { s_sel[i] = y; s_sel[o] = x; }
+      }
+      __syncthreads();
+    }
+  }
+
+  const float img_h = image_sizes[2 * b], img_w = image_sizes[2 * b + 1];
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const unsigned long long rec = s_sel[j];
+    const uint32_t r = (uint32_t)rec;
+    const float logit = float_from_ordered(~(uint32_t)(rec >> 32));
+    float x1, y1, x2, y2;
+    if (g.flat) {
+      const float4 p = ld_box(proposals_flat, (size_t)b * g.a_total + g.a_off[l] + r);
+      x1 = p.x; y1 = p.y; x2 = p.z; y2 = p.w;
+    } else {
+      const int a = r % A, rem = r / A;
+      const int y = rem / g.W[l], x = rem - y * g.W[l];
+      const float* d = g.del[l] + ((size_t)b * A * 4 + a * 4) * HW + rem;
+      const float dx = __ldg(d), dy = __ldg(d + HW);
+      float dw = __ldg(d + 2 * HW), dh = __ldg(d + 3 * HW);
+      const float sx = (float)(x * g.sw[l]), sy = (float)(y * g.sh[l]);
+      const float ax1 = __fadd_rn(sx, g.cell[l][a][0]), ay1 = __fadd_rn(sy, g.cell[l][a][1]);
+      const float ax2 = __fadd_rn(sx, g.cell[l][a][2]), ay2 = __fadd_rn(sy, g.cell[l][a][3]);
+      const float w = __fsub_rn(ax2, ax1), h = __fsub_rn(ay2, ay1);
+      const float cx = __fadd_rn(ax1, __fmul_rn(0.5f, w)), cy = __fadd_rn(ay1, __fmul_rn(0.5f, h));
+      dw = fminf(dw, g.xform_clip);
+      dh = fminf(dh, g.xform_clip);
+      const float pcx = __fadd_rn(__fmul_rn(dx, w), cx), pcy = __fadd_rn(__fmul_rn(dy, h), cy);
+      const float pw = __fmul_rn((float)exp((double)dw), w), ph = __fmul_rn((float)exp((double)dh), h);
+      const float hw = __fmul_rn(0.5f, pw), hh = __fmul_rn(0.5f, ph);
+      x1 = __fsub_rn(pcx, hw); y1 = __fsub_rn(pcy, hh);
+      x2 = __fadd_rn(pcx, hw); y2 = __fadd_rn(pcy, hh);
+    }
+    // clip_boxes_to_image (TV ops/boxes.py:149-182)
+    x1 = fminf(fmaxf(x1, 0.f), img_w); x2 = fminf(fmaxf(x2, 0.f), img_w);
+    y1 = fminf(fmaxf(y1, 0.f), img_h); y2 = fminf(fmaxf(y2, 0.f), img_h);
+    const float score = sigmoid_rn(logit);
+    // remove_small_boxes (TV ops/boxes.py:123-146) and the score filter (TV rpn.py:285)
+    const bool ok = (__fsub_rn(x2, x1) >= g.min_size) && (__fsub_rn(y2, y1) >= g.min_size) &&
+                    (score >= g.score_thresh);
+    const size_t pos = (size_t)b * g.k_tot + g.c_off[l] + j;
+    sbox[pos] = make_float4(x1, y1, x2, y2);
+    cscore[pos] = score;
+    alive[pos] = ok ? 1 : 0;
+    runkey[pos] = (uint32_t)(b * DGOD_MAX_LEVELS + l);
+  }
+}
+
+// Merge the per-level kept lists of an image by descending score (ties: lower level, then
+// earlier candidate — the stable order of the reference's sort) and emit the first post_nms.
+__global__ void __launch_bounds__(256)
+rpn_merge_kernel(const RpnDev g, int post_nms_top_n, const float4* __restrict__ sbox,
+                 const float* __restrict__ cscore, const int32_t* __restrict__ compact_pos,
+                 const int32_t* __restrict__ run_count, float* __restrict__ out_boxes,
+                 float* __restrict__ out_scores, int32_t* __restrict__ out_count) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) {
+    int tot = 0;
+    for (int l = 0; l < g.n_levels; ++l) tot += run_count[b * DGOD_MAX_LEVELS + l];
+    out_count[b] = min(tot, post_nms_top_n);
+  }
+  if (t >= g.k_tot) return;
+  int l = 0;
+  while (l + 1 < g.n_levels && t >= g.c_off[l + 1]) ++l;
+  const int j = t - g.c_off[l];
+  if (j >= run_count[b * DGOD_MAX_LEVELS + l]) return;
+  const size_t img0 = (size_t)b * g.k_tot;
+  const int pos = compact_pos[img0 + g.c_off[l] + j];
+  const float s = cscore[pos];
+  int rank = j;
+  for (int o = 0; o < g.n_levels; ++o) {
+    if (o == l) continue;
+    const int cnt = run_count[b * DGOD_MAX_LEVELS + o];
+    const int32_t* lst = compact_pos + img0 + g.c_off[o];
+    int lo = 0, hi = cnt;  // scores along lst are non-increasing
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const float v = cscore[lst[mid]];
+      const bool before = o < l ? (v >= s) : (v > s);
+      if (before) lo = mid + 1; else hi = mid;
+    }
+    rank += lo;
+  }
+  if (rank < post_nms_top_n) {
+    reinterpret_cast<float4*>(out_boxes)[(size_t)b * post_nms_top_n + rank] = sbox[pos];
+    out_scores[(size_t)b * post_nms_top_n + rank] = s;
+  }
+}
+
+struct RpnBuffers {
+  float4* sbox; float* cscore; uint8_t* alive; uint32_t* runkey; int32_t* compact;
+  int32_t* run_count; unsigned long long* keepbits; unsigned long long* mask;
+};
+
+static int fill_geometry(const dgod_rpn_config* cfg, RpnDev& g, int flat) {
+  DGOD_REQUIRE(cfg, "rpn: cfg is null");
+  DGOD_REQUIRE(cfg->n_levels >= 1 && cfg->n_levels <= DGOD_MAX_LEVELS, "rpn: n_levels out of range");
+  DGOD_REQUIRE(cfg->anchors_per_loc >= 1 && cfg->anchors_per_loc <= DGOD_MAX_CELL_ANCHORS,
+               "rpn: anchors_per_loc out of range");
+  DGOD_REQUIRE(cfg->n_img >= 0 && cfg->pre_nms_top_n > 0 && cfg->post_nms_top_n > 0, "rpn: bad sizes");
+  DGOD_REQUIRE(cfg->pre_nms_top_n <= 8192, "rpn: pre_nms_top_n > 8192 is not supported");
+  g.n_levels = cfg->n_levels; g.A = cfg->anchors_per_loc; g.n_img = cfg->n_img; g.flat = flat;
+  g.min_size = cfg->min_size; g.score_thresh = cfg->score_thresh; g.xform_clip = cfg->bbox_xform_clip;
+  int ao = 0, co = 0;
+  for (int l = 0; l < cfg->n_levels; ++l) {
+    DGOD_REQUIRE(cfg->height[l] > 0 && cfg->width[l] > 0, "rpn: empty feature level");
+    g.H[l] = cfg->height[l]; g.W[l] = cfg->width[l];
+    g.sh[l] = cfg->stride_h[l]; g.sw[l] = cfg->stride_w[l];
+    g.n_l[l] = cfg->height[l] * cfg->width[l] * cfg->anchors_per_loc;
+    g.k_l[l] = g.n_l[l] < cfg->pre_nms_top_n ? g.n_l[l] : cfg->pre_nms_top_n;
+    g.a_off[l] = ao; g.c_off[l] = co;
+    ao += g.n_l[l]; co += g.k_l[l];
+    for (int a = 0; a < cfg->anchors_per_loc; ++a)
+      for (int c = 0; c < 4; ++c) g.cell[l][a][c] = cfg->cell_anchors[l][a][c];
+  }
+  g.a_total = ao; g.k_tot = co;
+  return DGOD_OK;
+}
+
+static size_t carve_rpn(Workspace& ws, RpnBuffers& b, const RpnDev& g) {
+  const size_t n_pos = (size_t)(g.n_img > 0 ? g.n_img : 1) * g.k_tot;
+  int max_k = 1;
+  for (int l = 0; l < g.n_levels; ++l) max_k = g.k_l[l] > max_k ? g.k_l[l] : max_k;
+  b.sbox = ws.take<float4>(n_pos);
+  b.cscore = ws.take<float>(n_pos);
+  b.alive = ws.take<uint8_t>(n_pos);
+  b.runkey = ws.take<uint32_t>(n_pos);
+  b.compact = ws.take<int32_t>(n_pos);
+  b.run_count = ws.take<int32_t>((size_t)(g.n_img > 0 ? g.n_img : 1) * DGOD_MAX_LEVELS);
+  b.keepbits = ws.take<unsigned long long>(n_pos / 64 + 1);
+  b.mask = ws.take<unsigned long long>(n_pos * nms_mask_row_words(max_k));
+  return ws.used;
+}
+
+static int rpn_run(const dgod_rpn_config* cfg, RpnDev& g, const float* proposals_flat,
+                   const float* objectness_flat, const float* image_sizes, float* out_boxes,
+                   float* out_scores, int32_t* out_count, void* workspace, size_t workspace_bytes,
+                   cudaStream_t st) {
+  if (g.n_img == 0) return DGOD_OK;
+  DGOD_REQUIRE(image_sizes && out_boxes && out_scores && out_count, "rpn: null pointer");
+  Workspace ws(workspace, workspace_bytes);
+  RpnBuffers b;
+  carve_rpn(ws, b, g);
+  if (!workspace || !ws.ok()) {
+    set_error("rpn: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
+    return DGOD_ERR_WORKSPACE;
+  }
+  const int n_pos = g.n_img * g.k_tot;
+  int max_k = 1;
+  for (int l = 0; l < g.n_levels; ++l) max_k = g.k_l[l] > max_k ? g.k_l[l] : max_k;
+  int kp = 1;
+  while (kp < max_k) kp <<= 1;
+  const size_t smem = (size_t)kp * sizeof(unsigned long long);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DGOD_CUDA(cudaFuncSetAttribute(rpn_topk_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   8192 * (int)sizeof(unsigned long long)));
+    attr_set = true;
+  }
+  const size_t post = (size_t)cfg->post_nms_top_n;
+  DGOD_CUDA(cudaMemsetAsync(out_boxes, 0, (size_t)g.n_img * post * 4 * sizeof(float), st));
+  DGOD_CUDA(cudaMemsetAsync(out_scores, 0, (size_t)g.n_img * post * sizeof(float), st));
+  DGOD_CUDA(cudaMemsetAsync(b.keepbits, 0, ((size_t)n_pos / 64 + 1) * sizeof(unsigned long long), st));
+  DGOD_CUDA(cudaMemsetAsync(b.run_count, 0, (size_t)g.n_img * DGOD_MAX_LEVELS * sizeof(int32_t), st));
+
+  rpn_topk_decode_kernel<<<dim3(g.n_levels, g.n_img), kTopkThreads, smem, st>>>(
+      g, proposals_flat, objectness_flat, image_sizes, b.sbox, b.cscore, b.alive, b.runkey);
+  DGOD_LAUNCHED();
+  int rc = launch_nms_mask(b.sbox, b.runkey, n_pos, max_k, float_round_down(cfg->nms_thresh), b.mask, st);
+  if (rc) return rc;
+  rc = launch_nms_scan(b.mask, b.runkey, b.alive, n_pos, max_k, b.keepbits, b.compact, b.run_count, st);
+  if (rc) return rc;
+  rpn_merge_kernel<<<dim3(cdiv(g.k_tot, 256), g.n_img), 256, 0, st>>>(
+      g, cfg->post_nms_top_n, b.sbox, b.cscore, b.compact, b.run_count, out_boxes, out_scores, out_count);
+  DGOD_LAUNCHED();
+  return DGOD_OK;
+}
+
+}  // namespace dgod
+
+using namespace dgod;
+
+extern "C" size_t dgod_rpn_workspace_bytes(const dgod_rpn_config* cfg) {
+  RpnDev g;
+  if (fill_geometry(cfg, g, 0) != DGOD_OK) return 0;
+  Workspace ws(nullptr, 0);
+  RpnBuffers b;
+  return carve_rpn(ws, b, g);
+}
+
+extern "C" int dgod_rpn_proposals(const dgod_rpn_config* cfg, const float* const* objectness,
+                                  const float* const* deltas, const float* image_sizes,
+                                  float* out_boxes, float* out_scores, int32_t* out_count,
+                                  void* workspace, size_t workspace_bytes, dgod_stream_t stream) {
+  RpnDev g;
+  int rc = fill_geometry(cfg, g, 0);
+  if (rc) return rc;
+  DGOD_REQUIRE(objectness && deltas, "dgod_rpn_proposals: null pointer array");
+  for (int l = 0; l < g.n_levels; ++l) {
+    DGOD_REQUIRE(g.n_img == 0 || (objectness[l] && deltas[l]), "dgod_rpn_proposals: null level pointer");
+    g.obj[l] = objectness[l];
+    g.del[l] = deltas[l];
+  }
+  return rpn_run(cfg, g, nullptr, nullptr, image_sizes, out_boxes, out_scores, out_count, workspace,
+                 workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int dgod_rpn_filter(const dgod_rpn_config* cfg, const float* proposals,
+                               const float* objectness, const float* image_sizes, float* out_boxes,
+                               float* out_scores, int32_t* out_count, void* workspace,
+                               size_t workspace_bytes, dgod_stream_t stream) {
+  RpnDev g;
+  int rc = fill_geometry(cfg, g, 1);
+  if (rc) return rc;
+  DGOD_REQUIRE(g.n_img == 0 || (proposals && objectness), "dgod_rpn_filter: null pointer");
+  for (int l = 0; l < DGOD_MAX_LEVELS; ++l) { g.obj[l] = nullptr; g.del[l] = nullptr; }
+  return rpn_run(cfg, g, proposals, objectness, image_sizes, out_boxes, out_scores, out_count,
+                 workspace, workspace_bytes, (cudaStream_t)stream);
+}
