@@ -231,7 +231,7 @@ nms_prepare_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
   if (p < n_total && (!valid || valid[p])) {
     const int seg = find_segment(seg_offsets, n_seg, p);
     long long g = groups ? groups[p] : 0;
-    if (g < 0 || g > 65535) { atomicOr(status, 1); g = 0; }
+    if (!offset_mode && (g < 0 || g > 65535)) { atomicOr(status, 1); g = 0; }
     if (offset_mode) {
       float4 b = ld_box(boxes, p);
       float m = fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w));  // boxes.max(), TV ops/boxes.py:99
@@ -239,7 +239,7 @@ nms_prepare_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
       g = 0;  // one run per segment; the groups act through the coordinate shift only
     }
     key = ((unsigned long long)seg << 48) | ((unsigned long long)g << 32) |
-          (unsigned long long)(~float_ordered(scores[p]));
+          (unsigned long long)(~float_ordered(scores[p] + 0.f));  // -0 sorts like +0
   }
   keys[p] = key;
   vals[p] = (uint32_t)p;

@@ -1,0 +1,400 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+Bit-exact for integer / index work; RoIAlign within 1e-5 (fp32) / 1e-2 (bf16)."""
+import numpy as np
+import pytest
+import torch
+
+from dgod_b200 import synth
+from oracle import cpu as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _boxes(n, seed, h=800, w=1333):
+    return synth.random_boxes(n, h, w, synth.gen(seed))
+
+
+def _ops():
+    from dgod_b200 import ops
+    return ops
+
+
+# ------------------------------------------------------------------------------- box_iou / Matcher
+@pytest.mark.parametrize("m,n", [(1, 1), (20, 777), (100, 2000)])
+def test_box_iou_bit_exact(m, n):
+    a, b = _boxes(m, 0), _boxes(n, 1)
+    got = _ops().box_iou(a.to(DEV), b.to(DEV)).cpu().numpy()
+    ref = O.box_iou(a.numpy(), b.numpy())
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("m,n,hi,lo,lq", [(20, 5000, 0.7, 0.3, True), (100, 2000, 0.5, 0.5, False), (1, 300, 0.7, 0.3, True), (300, 999, 0.6, 0.2, True)])
+def test_matcher_on_matrix(m, n, hi, lo, lq):
+    ops = _ops()
+    q = O.box_iou(_boxes(m, 2).numpy(), _boxes(n, 3).numpy())
+    got = ops.Matcher(hi, lo, lq)(torch.from_numpy(q).to(DEV)).cpu().numpy()
+    assert np.array_equal(got, O.matcher(q, hi, lo, lq))
+
+
+def test_matcher_errors_and_edges():
+    ops = _ops()
+    with pytest.raises(ValueError, match="No ground-truth"):
+        ops.Matcher(0.5, 0.5)(torch.zeros((0, 5), device=DEV))
+    with pytest.raises(ValueError, match="No proposal"):
+        ops.Matcher(0.5, 0.5)(torch.zeros((5, 0), device=DEV))
+    q = np.array([[np.float32(0.7), np.float32(0.3), 0.29999998, 0.0, 0.2, 0.2],
+                  [0.0, 0.0, 0.0, 0.0, 0.0, 0.0]], dtype=np.float32)
+    got = ops.Matcher(0.7, 0.3, True)(torch.from_numpy(q).to(DEV)).cpu().numpy()
+    assert np.array_equal(got, O.matcher(q, 0.7, 0.3, True))
+
+
+@pytest.mark.parametrize("gts", [[20, 20], [20, 0, 1, 300], [5]])
+def test_fused_rpn_labels(gts):
+    ops = _ops()
+    anchors = _boxes(50000, 4, 608, 1024)
+    gt = [_boxes(m, 10 + i, 608, 1024) for i, m in enumerate(gts)]
+    out = ops.match_boxes([g.to(DEV) for g in gt], anchors.to(DEV), 0.7, 0.3, True,
+                          want=("labels_f32", "matched_boxes"))
+    for i, g in enumerate(gt):
+        idx, lab, mb = O.rpn_assign(g.numpy(), anchors.numpy(), 0.7, 0.3)
+        assert np.array_equal(out["matched_idx"][i].cpu().numpy(), idx)
+        assert np.array_equal(out["labels_f32"][i].cpu().numpy(), lab)
+        assert np.array_equal(out["matched_boxes"][i].cpu().numpy(), mb)
+
+
+def test_fused_roi_labels():
+    ops = _ops()
+    gts, props = [20, 0, 3], [2020, 1500, 2003]
+    gt = [_boxes(m, 20 + i, 608, 1024) for i, m in enumerate(gts)]
+    lab = [torch.randint(1, 9, (m,), generator=synth.gen(30 + i)) for i, m in enumerate(gts)]
+    pr = [torch.cat([_boxes(n - m, 40 + i, 608, 1024), g]) for i, (n, m, g) in enumerate(zip(props, gts, gt))]
+    out = ops.match_boxes([g.to(DEV) for g in gt], [p.to(DEV) for p in pr], 0.5, 0.5, False,
+                          gt_labels=[l.to(DEV) for l in lab], want=("labels_i64", "clamped_idx"))
+    off = 0
+    for g, l, p in zip(gt, lab, pr):
+        ci, lb = O.roi_assign(g.numpy(), l.numpy(), p.numpy(), 0.5, 0.5)
+        assert np.array_equal(out["clamped_idx"][off:off + len(p)].cpu().numpy(), ci)
+        assert np.array_equal(out["labels_i64"][off:off + len(p)].cpu().numpy(), lb)
+        off += len(p)
+
+
+# ------------------------------------------------------------------------------- FCOS
+def _fcos_anchors(h, w):
+    out, npl = [], []
+    for s in (8, 16, 32, 64, 128):
+        gh, gw = -(-h // s), -(-w // s)
+        cell = np.array([[-s * 4, -s * 4, s * 4, s * 4]], np.float32)  # anchor size 8*stride (fcos.py:467-469)
+        out.append(O.grid_anchors(cell, gh, gw, s, s))
+        npl.append(gh * gw)
+    return np.concatenate(out), npl
+
+
+@pytest.mark.parametrize("gts", [[20, 20], [0, 1, 2, 20], [300]])
+def test_fcos_assign_bit_exact(gts):
+    ops = _ops()
+    anchors, npl = _fcos_anchors(608, 1024)
+    gt = [_boxes(m, 50 + i, 608, 1024) for i, m in enumerate(gts)]
+    # equal quirky areas (fcos.py:543) force real ties in 1e8 - area
+    if gts[0] >= 2:
+        gt[0][1] = gt[0][0] + torch.tensor([3.0, 0.0, 3.0, 0.0])
+    lab = [torch.randint(1, 9, (m,), generator=synth.gen(60 + i)) for i, m in enumerate(gts)]
+    idx, cls, bt, oh = ops.fcos_assign(torch.from_numpy(anchors).to(DEV), [g.to(DEV) for g in gt], npl, 1.5,
+                                       gt_labels=[l.to(DEV) for l in lab], num_classes=9)
+    plain = ops.fcos_assign(torch.from_numpy(anchors).to(DEV), [g.to(DEV) for g in gt], npl, 1.5)
+    assert torch.equal(plain, idx)
+    for i, (g, l) in enumerate(zip(gt, lab)):
+        ri, rc, rb = O.fcos_assign(anchors, npl[0], npl[-1], g.numpy(), l.numpy(), 1.5)
+        assert np.array_equal(idx[i].cpu().numpy(), ri)
+        assert np.array_equal(cls[i].cpu().numpy(), rc)
+        assert np.array_equal(bt[i].cpu().numpy(), rb)
+        onehot = np.zeros((len(ri), 9), np.float32)
+        fg = rc >= 0
+        onehot[np.nonzero(fg)[0], rc[fg]] = 1.0
+        assert np.array_equal(oh[i].cpu().numpy(), onehot)
+    assert (idx.cpu().numpy() >= 0).sum() > 0
+
+
+# ------------------------------------------------------------------------------- NMS
+@pytest.mark.parametrize("n,thr", [(1, 0.5), (2, 0.5), (63, 0.5), (64, 0.3), (65, 0.7), (1000, 0.7), (4097, 0.6), (9000, 0.7), (20000, 0.5)])
+def test_nms_bit_exact(n, thr):
+    boxes = _boxes(n, n)
+    scores = torch.rand(n, generator=synth.gen(n + 1))  # fp32 rand: ties appear for large n (stable order)
+    got = _ops().nms(boxes.to(DEV), scores.to(DEV), thr).cpu().numpy()
+    assert np.array_equal(got, O.nms(boxes.numpy(), scores.numpy(), thr))
+
+
+def test_nms_edges():
+    ops = _ops()
+    assert ops.nms(torch.zeros((0, 4), device=DEV), torch.zeros(0, device=DEV), 0.5).shape == (0,)
+    b = torch.tensor([[0, 0, 10, 10], [20, 20, 30, 30], [40, 40, 50, 50], [60, 60, 70, 70]], dtype=torch.float32)
+    for s in ([0.5, 0.5, 0.5, 0.5], [0.3, 0.9, 0.3, 0.9]):
+        s = torch.tensor(s)
+        assert ops.nms(b.to(DEV), s.to(DEV), 0.5).tolist() == O.nms(b.numpy(), s.numpy(), 0.5).tolist()
+    s = torch.tensor([0.9, 0.8])
+    for bb, thr in (([[0, 0, 2, 1], [0, 0, 1, 1]], 0.5), ([[0, 0, 5, 1], [0, 0, 3, 1]], 0.6), ([[0, 0, 10, 1], [0, 0, 7, 1]], 0.7)):
+        bb = torch.tensor(bb, dtype=torch.float32)
+        assert ops.nms(bb.to(DEV), s.to(DEV), thr).tolist() == O.nms(bb.numpy(), s.numpy(), thr).tolist()
+    dup = torch.tensor([[0, 0, 5, 5]] * 200, dtype=torch.float32)
+    sc = torch.linspace(0, 1, 200)
+    assert ops.nms(dup.to(DEV), sc.to(DEV), 0.5).tolist() == [199]
+    assert ops.nms(dup.to(DEV), torch.ones(200, device=DEV), 0.5).tolist() == [0]
+
+
+@pytest.mark.parametrize("n,groups,thr", [(300, 3, 0.5), (1000, 5, 0.7), (1001, 5, 0.7), (4096, 8, 0.5), (5000, 9, 0.6), (8819, 5, 0.7), (30000, 5, 0.7)])
+def test_batched_nms_bit_exact(n, groups, thr):
+    g = synth.gen(n)
+    boxes = _boxes(n, n + 7, 608, 1024)
+    scores = synth.distinct_scores(n, g)
+    idxs = torch.randint(0, groups, (n,), generator=g)
+    got = _ops().batched_nms(boxes.to(DEV), scores.to(DEV), idxs.to(DEV), thr).cpu().numpy()
+    assert np.array_equal(got, O.batched_nms(boxes.numpy(), scores.numpy(), idxs.numpy(), thr))
+
+
+def test_batched_nms_ties_large_group_ids_and_modes():
+    ops = _ops()
+    g = synth.gen(3)
+    n = 3000
+    boxes = _boxes(n, 5)
+    scores = torch.randint(0, 40, (n,), generator=g).float() / 40
+    idxs = torch.randint(0, 5, (n,), generator=g) * 1_000_003 - 17      # sparse / negative ids
+    got = ops.batched_nms(boxes.to(DEV), scores.to(DEV), idxs.to(DEV), 0.7).cpu().numpy()
+    assert np.array_equal(got, O.batched_nms(boxes.numpy(), scores.numpy(), idxs.numpy(), 0.7))
+    # coordinate-trick arithmetic (<= 1000 boxes) incl. its fp32 rounding
+    n = 900
+    boxes = _boxes(n, 6) * 37.3
+    scores = synth.distinct_scores(n, g)
+    idxs = torch.randint(0, 90, (n,), generator=g)
+    got = ops.batched_nms(boxes.to(DEV), scores.to(DEV), idxs.to(DEV), 0.5).cpu().numpy()
+    assert np.array_equal(got, O.batched_nms(boxes.numpy(), scores.numpy(), idxs.numpy(), 0.5, mode=1))
+    assert ops.batched_nms(torch.zeros((0, 4), device=DEV), torch.zeros(0, device=DEV),
+                           torch.zeros(0, dtype=torch.int64, device=DEV), 0.5).shape == (0,)
+
+
+def test_nms_segments_batch_with_valid_mask_and_truncation():
+    ops = _ops()
+    counts = [4096, 0, 1, 3333, 700]
+    g = synth.gen(11)
+    boxes = torch.cat([_boxes(c, 70 + i, 608, 1024) for i, c in enumerate(counts)])
+    n = boxes.shape[0]
+    scores = synth.distinct_scores(n, g)
+    groups = torch.randint(1, 9, (n,), generator=g)
+    valid = torch.rand(n, generator=g) > 0.3
+    keep, info = ops.nms_segments(boxes.to(DEV), scores.to(DEV), groups.to(DEV), counts, 0.5,
+                                  valid=valid.to(DEV), max_out_per_seg=100)
+    keep, info = keep.cpu().numpy(), info.cpu().numpy()
+    assert info[-1] == 0
+    off = 0
+    for s, c in enumerate(counts):
+        sl = slice(off, off + c)
+        vi = np.nonzero(valid[sl].numpy())[0]
+        ref = O.batched_nms(boxes[sl].numpy()[vi], scores[sl].numpy()[vi], groups[sl].numpy()[vi], 0.5, mode=0)
+        ref = vi[ref][:100]
+        assert info[s] == len(ref)
+        assert np.array_equal(keep[s, :len(ref)], ref)
+        off += c
+
+
+# ------------------------------------------------------------------------------- RoIAlign
+def _roi_cases(H, W, scale):
+    img_h, img_w = H / scale, W / scale
+    return torch.tensor([
+        [0, 10.3, 20.7, 200.2, 180.9], [1, 0, 0, img_w, img_h], [0, 50, 50, 50.2, 50.3],
+        [1, -30, -40, 60, 70], [0, img_w - 20, img_h - 20, img_w + 90, img_h + 80],
+        [1, img_w + 40, img_h + 40, img_w + 80, img_h + 90], [0, 100, 100, 100, 100]], dtype=torch.float32)
+
+
+@pytest.mark.parametrize("sr,aligned,scale,out", [(2, False, 0.25, 7), (2, False, 0.125, 7), (0, False, 0.25, 7), (2, True, 0.25, 7), (3, False, 0.0625, (5, 9)), (2, False, 0.25, 14)])
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_roi_align_forward_backward(sr, aligned, scale, out, nhwc):
+    ops = _ops()
+    H, W, C = 48, 64, 40
+    x = torch.randn(2, C, H, W, generator=synth.gen(0))
+    rois = torch.cat([_roi_cases(H, W, scale), synth.rois_from_boxes([_boxes(40, 1, H / scale, W / scale), _boxes(40, 2, H / scale, W / scale)])])
+    ph, pw = (out, out) if isinstance(out, int) else out
+    ref = O.roi_align_fwd(x.numpy(), rois.numpy(), scale, ph, pw, sr, aligned)
+    xd = x.to(DEV)
+    if nhwc:
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    xd.requires_grad_(True)
+    got = ops.roi_align(xd, rois.to(DEV), out, scale, sr, aligned)
+    np.testing.assert_allclose(got.detach().cpu().numpy(), ref, rtol=1e-5, atol=1e-6)
+    go = torch.randn(ref.shape, generator=synth.gen(5))
+    got.backward(go.to(DEV))
+    gref = O.roi_align_bwd(go.numpy(), tuple(x.shape), rois.numpy(), scale, sr, aligned)
+    np.testing.assert_allclose(xd.grad.cpu().numpy(), gref, rtol=1e-5, atol=1e-5 * np.abs(gref).max())
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_multiscale_roi_align(dtype, tol, nhwc):
+    from dgod_b200.poolers import MultiScaleRoIAlign
+    img_h, img_w, C = 320, 416, 64
+    feats = synth.random_features(2, C, img_h, img_w, seed=3)
+    if dtype == torch.bfloat16:
+        feats = [f.to(dtype).float() for f in feats]     # oracle = fp32 on bf16-rounded inputs
+    sides = [111.99, 112.0, 112.01, 223.99, 224.0, 224.01, 447.9, 448.0, 448.1]
+    edge = torch.tensor([[3.0, 5.0, 3.0 + s, 5.0 + s] for s in sides])
+    boxes = [torch.cat([_boxes(150, 5, img_h, img_w), edge]), _boxes(130, 6, img_h, img_w)]
+    rois = synth.rois_from_boxes(boxes)
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+    ref = O.msroi_align_fwd([f.numpy() for f in feats], rois.numpy(), scales, 7, 7, 2, 2, 5)
+    pool = MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2)
+    x = {}
+    for i, f in enumerate(feats):
+        t = f.to(DEV).to(dtype)
+        if nhwc:
+            t = t.contiguous(memory_format=torch.channels_last)
+        x[str(i)] = t.requires_grad_(True)
+    x["pool"] = torch.zeros(2, C, 5, 7, device=DEV, dtype=dtype)
+    got = pool(x, [b.to(DEV) for b in boxes], [(img_h, img_w)] * 2)
+    assert got.dtype == dtype and got.shape == ref.shape
+    scale_ref = np.abs(ref).max()
+    np.testing.assert_allclose(got.detach().float().cpu().numpy(), ref, rtol=tol, atol=tol * scale_ref)
+    assert pool.scales == scales
+    if dtype == torch.float32:
+        go = torch.randn(ref.shape, generator=synth.gen(9))
+        got.backward(go.to(DEV))
+        grads = O.msroi_align_bwd(go.numpy(), [tuple(f.shape) for f in feats], rois.numpy(), scales, 2, 2, 5)
+        for i, gr in enumerate(grads):
+            np.testing.assert_allclose(x[str(i)].grad.cpu().numpy(), gr, rtol=1e-5, atol=1e-5 * max(np.abs(gr).max(), 1e-3))
+
+
+def test_roi_align_empty_and_errors():
+    ops = _ops()
+    x = torch.randn(1, 8, 16, 16, device=DEV)
+    assert ops.roi_align(x, torch.zeros((0, 5), device=DEV), 7, 0.25, 2).shape == (0, 8, 7, 7)
+    with pytest.raises(RuntimeError, match="Tensor\\[K, 5\\]"):
+        ops.roi_align(x, torch.zeros((3, 4), device=DEV), 7)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.roi_align(x.cpu(), torch.zeros((1, 5)), 7)
+
+
+# ------------------------------------------------------------------------------- RPN pipeline
+def _rpn_case(B, img_h, img_w, seed, pre=600):
+    from torchvision.models.detection.anchor_utils import AnchorGenerator
+    g = synth.gen(seed)
+    ag = AnchorGenerator(((32,), (64,), (128,), (256,), (512,)), ((0.5, 1.0, 2.0),) * 5)
+    ph, pw = -(-img_h // 32) * 32, -(-img_w // 32) * 32
+    grids = [(-(-ph // s), -(-pw // s)) for s in (4, 8, 16, 32, 64)]
+    strides = [(ph // h, pw // w) for h, w in grids]
+    obj = [torch.randn(B, 3, h, w, generator=g) for h, w in grids]
+    dl = [torch.randn(B, 12, h, w, generator=g) * 0.3 for h, w in grids]
+    cell = [c.tolist() for c in ag.cell_anchors]
+    return obj, dl, grids, strides, cell
+
+
+def _flatten_like_torchvision(obj, dl):
+    B = obj[0].shape[0]
+    o = torch.cat([x.permute(0, 2, 3, 1).reshape(B, -1) for x in obj], 1)
+    d = torch.cat([x.view(B, -1, 4, x.shape[2], x.shape[3]).permute(0, 3, 4, 1, 2).reshape(B, -1, 4) for x in dl], 1)
+    return o, d
+
+
+@pytest.mark.parametrize("B,img,pre,post", [(2, (300, 500), 600, 500), (3, (600, 999), 2000, 2000)])
+def test_rpn_proposals_fused(B, img, pre, post):
+    ops = _ops()
+    obj, dl, grids, strides, cell = _rpn_case(B, img[0], img[1], 5, pre)
+    sizes = torch.tensor([[img[0], img[1]]] * B, dtype=torch.float32)
+    boxes, scores, counts = ops.rpn_proposals([o.to(DEV) for o in obj], [d.to(DEV) for d in dl], sizes.to(DEV),
+                                              strides, cell, pre, post, 0.7, 1e-3, 0.0)
+    boxes, scores, counts = boxes.cpu().numpy(), scores.cpu().numpy(), counts.cpu().numpy()
+    o_flat, d_flat = _flatten_like_torchvision(obj, dl)
+    anchors = np.concatenate([O.grid_anchors(np.array(cell[l], np.float32), h, w, strides[l][0], strides[l][1])
+                              for l, (h, w) in enumerate(grids)])
+    npl = [3 * h * w for h, w in grids]
+    for i in range(B):
+        props = O.box_decode(d_flat[i].numpy(), anchors)
+        rb, rs = O.rpn_filter_image(props, o_flat[i].numpy(), npl, pre, post, 0.7, 1e-3, 0.0, img[0], img[1])
+        assert counts[i] == len(rb)
+        assert np.array_equal(boxes[i, :len(rb)], rb)       # same exp/sigmoid definition -> bit-exact
+        assert np.array_equal(scores[i, :len(rb)], rs)
+        assert not boxes[i, len(rb):].any()
+
+
+def test_rpn_filter_on_decoded_proposals():
+    ops = _ops()
+    g = synth.gen(4)
+    npl = [3 * 38 * 64, 3 * 19 * 32, 3 * 10 * 16, 3 * 5 * 8, 3 * 3 * 4]
+    A = sum(npl)
+    props = torch.stack([synth.random_boxes(A, 330, 540, g), synth.random_boxes(A, 330, 540, g)]) - 15.0
+    obj = torch.randn(2, A, generator=g)
+    sizes = torch.tensor([[300.0, 500.0], [280.0, 500.0]])
+    boxes, scores, counts = ops.rpn_filter_proposals(props.to(DEV), obj.to(DEV), sizes.to(DEV), npl, 600, 500, 0.7)
+    for i in range(2):
+        rb, rs = O.rpn_filter_image(props[i].numpy(), obj[i].numpy(), npl, 600, 500, 0.7, 1e-3, 0.0,
+                                    float(sizes[i, 0]), float(sizes[i, 1]))
+        assert int(counts[i]) == len(rb)
+        assert np.array_equal(boxes[i, :len(rb)].cpu().numpy(), rb)
+        assert np.array_equal(scores[i, :len(rb)].cpu().numpy(), rs)
+
+
+def test_rpn_topk_with_massive_ties():
+    ops = _ops()
+    obj, dl, grids, strides, cell = _rpn_case(1, 300, 500, 9)
+    obj = [torch.zeros_like(o) for o in obj]            # every logit equal: ties resolved by anchor index
+    obj[0][0, 1, 3, 5] = 1.0
+    sizes = torch.tensor([[300.0, 500.0]])
+    boxes, scores, counts = ops.rpn_proposals([o.to(DEV) for o in obj], [d.to(DEV) for d in dl], sizes.to(DEV),
+                                              strides, cell, 300, 200, 0.7)
+    o_flat, d_flat = _flatten_like_torchvision(obj, dl)
+    anchors = np.concatenate([O.grid_anchors(np.array(cell[l], np.float32), h, w, strides[l][0], strides[l][1])
+                              for l, (h, w) in enumerate(grids)])
+    rb, rs = O.rpn_filter_image(O.box_decode(d_flat[0].numpy(), anchors), o_flat[0].numpy(),
+                                [3 * h * w for h, w in grids], 300, 200, 0.7, 1e-3, 0.0, 300, 500)
+    assert int(counts[0]) == len(rb)
+    assert np.array_equal(boxes[0, :len(rb)].cpu().numpy(), rb)
+
+
+# ------------------------------------------------------------------------------- post-processing, GRL
+def test_detect_candidates_decode_and_grl():
+    ops = _ops()
+    g = synth.gen(8)
+    per = [512, 300]
+    n, ncls = sum(per), 9
+    props = synth.random_boxes(n, 600, 1000, g)
+    logits, reg = torch.randn(n, ncls, generator=g) * 2, torch.randn(n, ncls * 4, generator=g) * 0.5
+    sizes = torch.tensor([[600.0, 1000.0], [580.0, 990.0]])
+    cb, cs, cl, cv = ops.detect_candidates(logits.to(DEV), reg.to(DEV), props.to(DEV), per, sizes.to(DEV))
+    off = 0
+    for i, c in enumerate(per):
+        rb, rs, rl, rv = O.detect_candidates(logits[off:off + c].numpy(), reg[off:off + c].numpy(),
+                                             props[off:off + c].numpy(), float(sizes[i, 0]), float(sizes[i, 1]))
+        assert np.array_equal(cb[off:off + c].cpu().numpy(), rb)
+        assert np.array_equal(cs[off:off + c].cpu().numpy(), rs)
+        assert np.array_equal(cl[off:off + c].cpu().numpy(), rl)
+        assert np.array_equal(cv[off:off + c].cpu().numpy(), rv)
+        off += c
+    dec = ops.box_decode(reg.to(DEV), props.to(DEV), (10.0, 10.0, 5.0, 5.0)).cpu().numpy()
+    assert np.array_equal(dec, O.box_decode(reg.numpy(), props.numpy(), (10.0, 10.0, 5.0, 5.0)))
+    for shape in [(1000,), (513, 1024), (7,)]:
+        x = torch.randn(*shape, generator=g)
+        xd = x.to(DEV).requires_grad_(True)
+        y = ops.grad_reverse(xd)
+        assert torch.equal(y, xd)
+        go = torch.randn(*shape, generator=g)
+        y.backward(go.to(DEV))
+        assert np.array_equal(xd.grad.cpu().numpy(), O.grl_scale(go.numpy(), 0.1))
+    xb = torch.randn(4097, generator=g).to(torch.bfloat16)
+    xd = xb.to(DEV).requires_grad_(True)
+    ops.grad_reverse(xd).backward(xb.to(DEV))
+    assert torch.equal(xd.grad.cpu(), (xb.neg() * 0.1))
+
+
+def test_grl_linear_matches_unfused():
+    ops = _ops()
+    g = synth.gen(12)
+    x = torch.randn(1024, 1024, generator=g).to(DEV).requires_grad_(True)
+    lin = torch.nn.Linear(1024, 512).to(DEV)
+    go = torch.randn(1024, 512, generator=g).to(DEV)
+    y1 = ops.grl_linear(x, lin.weight, lin.bias)
+    y1.backward(go)
+    g1, gw1 = x.grad.clone(), lin.weight.grad.clone()
+    x.grad = None
+    lin.weight.grad = None
+    y2 = lin(ops.grad_reverse(x))
+    y2.backward(go)
+    assert torch.equal(y1, y2)
+    torch.testing.assert_close(g1, x.grad, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(gw1, lin.weight.grad, rtol=1e-5, atol=1e-5)
