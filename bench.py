@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Benchmark of the DGOD hot path: DGFRCNN dg-mode training images/s (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+A *step* is one pass of the reference's 8-training-step mode cycle (0,1,0,2,0,3,0,4 —
+DGFRCNN.py:125-199) over synthetic 3x800x1333 batches: 8*B images per GPU, optimizer step included
+in every training step.  One JSON line is printed by rank 0.
+  value     whole-job images/s with the batches resident in HBM, CUDA-event timed, max over ranks
+  e2e       the same loop fed from pinned host memory (H2D of images+targets and D2H of the loss
+            inside the timed region)
+  roofline  the dominant dgod_b200 kernel: algorithmic bytes / CUDA-event time of its launches in
+            the timed region vs the measured HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline (N=1) the oracle port of the reference on the host cores, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+IMG_H, IMG_W, N_GT = 800, 1333, 20
+REG_WEIGHTS = [0.5, 0.5, 0.5, 0.05, 0.0001]
+CYCLE = (0, 1, 0, 2, 0, 3, 0, 4)
+# The reference fine-tunes COCO-pretrained weights at lr 2e-3 (DGFRCNN.py:85,99); those weights
+# cannot be downloaded here and a random-init detector collapses after one step at that rate (the
+# RPN then proposes <512 boxes and the sampled work disappears).  Both arms therefore run the same
+# SGD update kernels with a tiny rate so that every step does the full, representative work.
+BENCH_LR = 1e-5
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--batch", type=int, default=8, help="images per GPU per training step")
+    p.add_argument("--domains", type=int, default=0, help="source domains (default 2 at N=1, 3 at N>1)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+# --------------------------------------------------------------------------------------------- helpers
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.thread, self.gpu = [], None, None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synthetic_batches(n_batches, batch, n_domains, seed0, pin=False):
+    """DrivingDataset-shaped tuples (DrivingDataset.py:71 / DGcommon.collate_fn): images float
+    [3,800,1333] in [0,1), boxes, labels 1..8, domain = i mod D.  Seeds 1000*rank + batch index."""
+    import torch
+    from dgod_b200 import synth
+    out = []
+    for j in range(n_batches):
+        imgs = synth.random_images(batch, IMG_H, IMG_W, seed0 + j)
+        targets, dom = synth.random_targets(batch, N_GT, IMG_H, IMG_W, seed0 + j, n_domains)
+        boxes = [t["boxes"] for t in targets]
+        labels = [t["labels"] for t in targets]
+        if pin:
+            imgs = [i.pin_memory() for i in imgs]
+            boxes = [b.pin_memory() for b in boxes]
+            labels = [l.pin_memory() for l in labels]
+            dom = dom.pin_memory()
+        out.append((imgs, boxes, labels, dom))
+    return out
+
+
+def to_device(batch, dev):
+    imgs, boxes, labels, dom = batch
+    return ([i.to(dev, non_blocking=True) for i in imgs], [b.to(dev, non_blocking=True) for b in boxes],
+            [l.to(dev, non_blocking=True) for l in labels], dom.to(dev, non_blocking=True))
+
+
+def batch_bytes(batch):
+    imgs, boxes, labels, dom = batch
+    return sum(t.numel() * t.element_size() for t in (*imgs, *boxes, *labels, dom))
+
+
+def measured_hbm_peak():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def calibrate(model, imgs):
+    """Random init with calibrated frozen-BN statistics (dgod_b200/utils.py) — both arms."""
+    import torch
+    from dgod_b200.utils import calibrate_frozen_bn
+    det = model.detector
+    with torch.no_grad():
+        image_list, _ = det.transform([i for i in imgs[:2]], None)
+        calibrate_frozen_bn(det.backbone, image_list.tensors)
+
+
+# --------------------------------------------------------------------------------------------- CUDA arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from dgod_b200 import _lib, ops
+    from dgod_b200.dg import DGFRCNN, allreduce_gradients
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the dgod_b200 path has no CPU fallback")
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_dom = args.domains or (2 if world == 1 else 3)
+    B = args.batch
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(0)
+    model = DGFRCNN(9, B, "dg", REG_WEIGHTS, n_dom).to(dev).train()
+    host = synthetic_batches(4, B, n_dom, 1000 * rank, pin=True)
+    resident = [to_device(b, dev) for b in host]
+    calibrate(model, resident[0][0])
+    if world > 1:
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, 0)
+    opt = model.configure_optimizer(lr=BENCH_LR)
+    params = [p for p in model.parameters()]
+    torch.cuda.synchronize()
+
+    def train_step(batch):
+        loss = model.training_step(batch)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        allreduce_gradients(params, world)
+        opt.step()
+        return loss
+
+    def cycle(from_host: bool):
+        last = None
+        for s in range(len(CYCLE)):
+            b = host[(s // 2) % 4] if from_host else resident[(s // 2) % 4]
+            if from_host:
+                b = to_device(b, dev)
+            last = train_step(b)
+            if from_host:
+                last = last.item()          # D2H read of the step's result
+        return last
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_cycles: int, from_host: bool):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_cycles):
+            cycle(from_host)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        cycle(False)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ops.KernelTimer.enabled = True
+    ops.KernelTimer.reset()
+    launches0 = _lib.launch_count()
+    ms = timed(args.steps, False)
+    launches = _lib.launch_count() - launches0
+    final_loss = float(train_step(resident[0]).item())   # untimed: is the run still numerically sane?
+    model.mode = model.sub_mode = 0
+    ops.KernelTimer.enabled = False
+    kern = ops.KernelTimer.summary()
+    clk = clocks.stop() if rank == 0 else None
+    imgs_per_cycle = len(CYCLE) * B * world
+    value = args.steps * imgs_per_cycle / (ms / 1e3)
+
+    e2e = None
+    if not args.no_e2e:
+        cycle(True)
+        ms_e = timed(args.steps, True)
+        h2d = sum(batch_bytes(host[(s // 2) % 4]) for s in range(len(CYCLE)))
+        e2e = {"value": round(args.steps * imgs_per_cycle / (ms_e / 1e3), 3), "unit": "img/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * len(CYCLE), "ms_per_step": round(ms_e / args.steps, 3)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_hbm_peak()
+    roof, kernels = None, {}
+    for name, (n, tot_ms, tot_bytes) in kern.items():
+        gbs = tot_bytes / 1e9 / (tot_ms / 1e3) if tot_ms > 0 else 0.0
+        kernels[name] = {"launches": n, "avg_us": round(1e3 * tot_ms / max(n, 1), 2), "GB/s": round(gbs, 1),
+                         "share_of_step": round(tot_ms / ms, 4)}
+    if kern:
+        top = max((k for k in kern if k.startswith("msroi")), key=lambda k: kern[k][1], default=max(kern, key=lambda k: kern[k][1]))
+        n, tot_ms, tot_bytes = kern[top]
+        ach = tot_bytes / 1e9 / (tot_ms / 1e3)
+        roof = {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "launches": n, "avg_launch_us": round(1e3 * tot_ms / n, 2)}
+    out = {
+        "metric": "DGFRCNN dg train img/s", "value": round(value, 3), "unit": "img/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"DGFRCNN dg mode, {n_dom} synthetic source domains, instance+image domain classifiers "
+                               f"with GRL, batch {B}/GPU, R50-FPN random init, 3x{IMG_H}x{IMG_W} images (detector min/max "
+                               f"600/1200 -> 608x1024), {N_GT} GT/img; step = one 8-training-step mode cycle "
+                               f"0,1,0,2,0,3,0,4 incl. SGD steps ({len(CYCLE) * B} img/GPU)",
+                   "batch_per_gpu": B, "domains": n_dom, "parallelism": f"dp{world}",
+                   "cache": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no flush needed",
+                   "optimizer": f"SGD wd 5e-4 as DGFRCNN.py:98-104, lr {BENCH_LR} (random init diverges at the reference's 2e-3)",
+                   "backbone_math": "PyTorch defaults (cuDNN conv may use TF32, matmul fp32); hot-path kernels fp32"},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roof, "kernels": kernels,
+        "loss_finite": bool(torch.isfinite(torch.as_tensor(final_loss)).all()),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_reference_sample(1, 1)["cpu_baseline"]
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_sample(steps: int, warmup: int):
+    """The reference's CPU path (oracle/ref_dgfrcnn.py on stock torchvision CPU ops), bounded:
+    one step = one full dg mode cycle at batch 1 (8 images of 3x800x1333), all host threads."""
+    import torch
+    from oracle.ref_dgfrcnn import RefDGFRCNN
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = RefDGFRCNN(9, 1, REG_WEIGHTS, 2).train()
+    batches = synthetic_batches(4, 1, 2, 0)
+    calibrate(model, batches[0][0] + batches[1][0])
+    opt = model.configure_optimizer(lr=BENCH_LR)
+
+    def step(b):
+        loss = model.training_step(b)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+
+    for _ in range(warmup):            # one untimed mode-0 step is enough to warm the allocator
+        step(batches[0])
+        model.step_index = 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for s in range(len(CYCLE)):
+            step(batches[(s // 2) % 4])
+    dt = time.perf_counter() - t0
+    n_img = steps * len(CYCLE)
+    v = n_img / dt
+    return {"value": v, "ms_per_step": 1e3 * dt / steps,
+            "cpu_baseline": {"value": round(v, 4), "unit": "img/s", "cores": cores, "kind": "port",
+                             "sample": f"{steps} dg mode cycle(s) at batch 1 ({n_img} images of 3x{IMG_H}x{IMG_W}), "
+                                       f"oracle/ref_dgfrcnn.py on torchvision CPU ops, {cores} threads, "
+                                       f"{dt:.1f} s"}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
+    r = cpu_reference_sample(steps, warmup)
+    out = {
+        "impl": "reference", "metric": "DGFRCNN dg train img/s", "value": round(r["value"], 4), "unit": "img/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(r["ms_per_step"], 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "DGFRCNN dg mode on the host CPU: step = one 8-training-step mode cycle at batch 1 "
+                               f"(bounded sample of the GPU arm's workload, same 3x{IMG_H}x{IMG_W} synthetic images, "
+                               "same detector and schedule); steps/warmup capped at 3/1 to stay within minutes",
+                   "batch_per_gpu": 1, "domains": 2, "parallelism": "cpu"},
+        "cpu_baseline": r["cpu_baseline"],
+        "e2e": {"value": round(r["value"], 4), "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -1,0 +1,168 @@
+"""Generates tests/golden/*.npz by running the REFERENCE's own modules (imported unchanged from
+/root/reference) on seeded synthetic inputs.  Run here (the reference is not on the GPU box):
+
+    python -m oracle.gen_golden
+
+Fixtures:
+  fcos_assign.npz     fcos.FCOS.compute_loss (fcos.py:503-550) matched indices and
+                      fcos.FCOSHead.compute_loss (fcos.py:124-202) `gt_classes` one-hot
+  frcnn_hotpath.npz   fasterrcnn.RegionProposalNetworkWILDS / RoIHeadsWILDS (fasterrcnn.py:90-305) on
+                      synthetic FPN features: proposals, anchor labels, sampled RoI labels, pooled
+                      features checksum, per-image losses
+  frcnn_step.npz      per-image losses of a full fasterrcnn.FastWILDS train step vs the restated
+                      oracle.ref_dgfrcnn.RefFasterRCNN with identical weights and RNG
+"""
+from __future__ import annotations
+
+import sys
+import types
+import warnings
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+REF = Path("/root/reference")
+OUT = ROOT / "tests" / "golden"
+sys.path.insert(0, str(ROOT))
+
+from dgod_b200 import synth  # noqa: E402
+
+
+def import_reference():
+    if not REF.exists():
+        raise SystemExit("/root/reference is not available on this machine")
+    if str(REF) not in sys.path:
+        sys.path.insert(0, str(REF))
+    warnings.filterwarnings("ignore")
+    import fasterrcnn  # noqa
+    import fcos  # noqa
+    return fasterrcnn, fcos
+
+
+# ----------------------------------------------------------------------------------------- FCOS
+def fcos_inputs():
+    """Anchors of a 256x320 image on 5 levels (anchor size 8*stride, fcos.py:467-469) and GT lists
+    covering 0, 1, 2 and many boxes, with one pair of equal quirky areas."""
+    from oracle import cpu as O
+    anchors, npl = [], []
+    for s in (8, 16, 32, 64, 128):
+        gh, gw = -(-256 // s), -(-320 // s)
+        anchors.append(O.grid_anchors(np.array([[-4 * s, -4 * s, 4 * s, 4 * s]], np.float32), gh, gw, s, s))
+        npl.append(gh * gw)
+    anchors = np.concatenate(anchors)
+    gts, labels = [], []
+    for i, m in enumerate([12, 0, 1, 2, 40]):
+        g = synth.gen(100 + i)
+        b = synth.random_boxes(m, 256, 320, g, log_size=(2.0, 3.2))
+        if m >= 2:
+            b[1] = b[0] + torch.tensor([3.0, 0.0, 3.0, 0.0])
+        if m == 1:
+            b[0] = torch.tensor([60.0, 50.0, 160.0, 150.0])   # certainly matched: shows the `<= 1` rule
+        gts.append(b)
+        labels.append(torch.randint(1, 9, (m,), generator=g))
+    return anchors, npl, gts, labels
+
+
+def gen_fcos(fcos):
+    anchors, npl, gts, labels = fcos_inputs()
+    B, N = len(gts), len(anchors)
+    a = torch.from_numpy(anchors)
+    targets = [{"boxes": g, "labels": l} for g, l in zip(gts, labels)]
+    stub = types.SimpleNamespace(center_sampling_radius=1.5,
+                                 head=types.SimpleNamespace(compute_loss=lambda t, h, an, m: m))
+    matched = fcos.FCOS.compute_loss(stub, targets, None, [a] * B, npl)
+    head = types.SimpleNamespace(box_coder=fcos.BoxLinearCoder(normalize_by_size=True))
+    ho = {"cls_logits": torch.zeros(B, N, 9), "bbox_regression": torch.zeros(B, N, 4), "bbox_ctrness": torch.zeros(B, N, 1)}
+    loss = fcos.FCOSHead.compute_loss(head, targets, ho, [a] * B, [m.clone() for m in matched])
+    np.savez_compressed(OUT / "fcos_assign.npz", matched=torch.stack(matched).numpy(),
+                        gt_classes=loss["gt_classes"].numpy().astype(np.uint8))
+    print("fcos_assign.npz", torch.stack(matched).shape, int((torch.stack(matched) >= 0).sum()), "matched")
+
+
+# ----------------------------------------------------------------------------------------- Faster R-CNN hot path
+HOT = dict(img=(256, 320), batch=2, channels=256, n_gt=6, seed=7)
+
+
+def hotpath_inputs():
+    h, w = HOT["img"]
+    feats = synth.random_features(HOT["batch"], HOT["channels"], h, w, HOT["seed"], strides=(4, 8, 16, 32, 64))
+    features = {k: f * 0.1 for k, f in zip(["0", "1", "2", "3", "pool"], feats)}
+    targets, _ = synth.random_targets(HOT["batch"], HOT["n_gt"], h, w, HOT["seed"])
+    return features, targets
+
+
+def seeded_module_weights(mod: torch.nn.Module, seed: int):
+    g = synth.gen(seed)
+    with torch.no_grad():
+        for _, p in sorted(mod.named_parameters()):
+            p.copy_(torch.randn(p.shape, generator=g) * (0.02 if p.dim() > 1 else 0.01))
+
+
+def gen_hotpath(fasterrcnn):
+    from torchvision.models.detection.image_list import ImageList
+    h, w = HOT["img"]
+    features, targets = hotpath_inputs()
+    model = fasterrcnn.FastWILDS(types.SimpleNamespace(out_channels=256), num_classes=9,
+                                 rpn_pre_nms_top_n_train=600, rpn_post_nms_top_n_train=600)
+    seeded_module_weights(model.rpn, 1)
+    seeded_module_weights(model.roi_heads, 2)
+    model.train()
+    images = ImageList(torch.zeros(HOT["batch"], 3, h, w), [(h, w)] * HOT["batch"])
+    torch.manual_seed(1234)
+    proposals, rpn_losses = model.rpn(images, features, targets)
+    anchors = model.rpn.anchor_generator(images, list(features.values()))
+    labels, _ = model.rpn.assign_targets_to_anchors(anchors, targets)
+    grabbed = {}
+    model.roi_heads.box_head.register_forward_hook(lambda m, i, o: grabbed.update(labels=i[1], pooled=i[0]))
+    det, roi_losses = model.roi_heads(features, [p.detach() for p in proposals], images.image_sizes, targets)
+    np.savez_compressed(
+        OUT / "frcnn_hotpath.npz",
+        proposals=np.stack([p.detach().numpy() for p in proposals]),
+        anchor_labels=torch.stack(labels).numpy().astype(np.int8),
+        roi_labels=torch.stack(grabbed["labels"]).numpy(),
+        pooled_sum=grabbed["pooled"].detach().double().sum(dim=(1, 2, 3)).numpy(),
+        loss_objectness=rpn_losses["loss_objectness"].detach().numpy(),
+        loss_rpn_box_reg=rpn_losses["loss_rpn_box_reg"].detach().numpy(),
+        loss_classifier=roi_losses["loss_classifier"].detach().numpy(),
+        loss_box_reg=roi_losses["loss_box_reg"].detach().numpy(),
+        det_counts=np.array([len(d["boxes"]) for d in det]))
+    print("frcnn_hotpath.npz", [tuple(p.shape) for p in proposals], {k: v.tolist() for k, v in rpn_losses.items()})
+
+
+# ----------------------------------------------------------------------------------------- full step
+STEP = dict(img=(224, 288), batch=2, n_gt=5, seed=11, min_size=224, max_size=320)
+
+
+def gen_step(fasterrcnn):
+    from oracle.ref_dgfrcnn import RefFasterRCNN
+    torch.manual_seed(0)
+    ref = fasterrcnn.fasterrcnn_resnet50_fpn(num_classes=8, pretrained=False, pretrained_backbone=False,
+                                             min_size=STEP["min_size"], max_size=STEP["max_size"])
+    mine = RefFasterRCNN(9, STEP["min_size"], STEP["max_size"])
+    missing = mine.load_state_dict(ref.state_dict(), strict=True)
+    ref.train(), mine.train()
+    imgs = synth.random_images(STEP["batch"], *STEP["img"], STEP["seed"])
+    targets, _ = synth.random_targets(STEP["batch"], STEP["n_gt"], *STEP["img"], STEP["seed"])
+    out = {}
+    for name, model in (("ref", ref), ("mine", mine)):
+        torch.manual_seed(4321)
+        det = model([i.clone() for i in imgs], [{k: v.clone() for k, v in t.items()} for t in targets])
+        out[name] = {k: torch.stack([d["losses"][k] for d in det]).detach().numpy() for k in det[0]["losses"]}
+    for k in out["ref"]:
+        assert np.array_equal(out["ref"][k], out["mine"][k]), (k, out["ref"][k], out["mine"][k])
+    np.savez_compressed(OUT / "frcnn_step.npz", **out["ref"])
+    print("frcnn_step.npz restated step == reference step bit-for-bit:", {k: v.tolist() for k, v in out["ref"].items()}, missing)
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    fasterrcnn, fcos = import_reference()
+    gen_fcos(fcos)
+    gen_hotpath(fasterrcnn)
+    gen_step(fasterrcnn)
+
+
+if __name__ == "__main__":
+    main()
