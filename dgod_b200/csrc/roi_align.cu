@@ -161,8 +161,9 @@ int fill_roi_dev(const dgod_roi_config* cfg, RoiDev& g) {
 int msroi_fwd_fast(const dgod_roi_config* cfg, const RoiDev& g, const float* rois, int n_rois,
                    void* out, cudaStream_t st, int* handled);
 int msroi_bwd_fast(const dgod_roi_config* cfg, const RoiDev& g, const void* grad_out,
-                   const float* rois, int n_rois, const int32_t* roi_img_offsets, cudaStream_t st,
-                   int* handled);
+                   const float* rois, int n_rois, const int32_t* roi_img_offsets, void* workspace,
+                   size_t workspace_bytes, cudaStream_t st, int* handled);
+size_t msroi_bwd_workspace(int n_rois);
 
 }  // namespace dgod
 
@@ -196,10 +197,13 @@ extern "C" int dgod_msroi_align_fwd(const dgod_roi_config* cfg, const void* cons
   return DGOD_OK;
 }
 
+extern "C" size_t dgod_msroi_align_bwd_workspace_bytes(int n_rois) { return msroi_bwd_workspace(n_rois); }
+
 extern "C" int dgod_msroi_align_bwd(const dgod_roi_config* cfg, const void* grad_out,
                                     const float* rois, int n_rois,
                                     const int32_t* roi_img_offsets, void* const* grad_feats,
-                                    int algo, dgod_stream_t stream) {
+                                    int algo, void* workspace, size_t workspace_bytes,
+                                    dgod_stream_t stream) {
   RoiDev g;
   int rc = fill_roi_dev(cfg, g);
   if (rc) return rc;
@@ -216,7 +220,7 @@ extern "C" int dgod_msroi_align_bwd(const dgod_roi_config* cfg, const void* grad
   DGOD_REQUIRE(n_rois == 0 || (grad_out && rois), "roi_align: null pointer");
   if (algo != 1 && n_rois > 0) {
     int handled = 0;
-    rc = msroi_bwd_fast(cfg, g, grad_out, rois, n_rois, roi_img_offsets, st, &handled);
+    rc = msroi_bwd_fast(cfg, g, grad_out, rois, n_rois, roi_img_offsets, workspace, workspace_bytes, st, &handled);
     if (rc || handled) return rc;
     DGOD_REQUIRE(algo == 0, "roi_align: the tile-gather backward does not support this configuration");
   }

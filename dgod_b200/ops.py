@@ -437,7 +437,10 @@ def _msroi_bwd_op(grad: Tensor, rois: Tensor, roi_img_offsets: Optional[Tensor],
     ptrs, keep_alive = _level_ptrs(grads)
     esz = grad.element_size()
     tok = KernelTimer.start("msroi_align_bwd", n * c * pooled_h * pooled_w * esz + 20 * n + sum(g.numel() for g in grads) * esz)
-    check(lib.dgod_msroi_align_bwd(C.byref(cfg), _p(grad), _p(rois), n, _p(roi_img_offsets), ptrs, int(algo), _stream()))
+    wsb = lib.dgod_msroi_align_bwd_workspace_bytes(n)
+    ws = _ws(wsb, grad.device)
+    check(lib.dgod_msroi_align_bwd(C.byref(cfg), _p(grad), _p(rois), n, _p(roi_img_offsets), ptrs, int(algo),
+                                   _p(ws), wsb, _stream()))
     KernelTimer.stop(tok)
     return grads
 

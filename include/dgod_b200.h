@@ -192,14 +192,17 @@ typedef struct {
 int dgod_msroi_align_fwd(const dgod_roi_config* cfg /*host*/,
                          const void* const* feats /*host array of device ptrs*/,
                          const float* rois, int n_rois, void* out, dgod_stream_t stream);
-/* grad_feats[l] is fully overwritten (zero where no RoI contributes): no memset required. */
+size_t dgod_msroi_align_bwd_workspace_bytes(int n_rois);
+/* grad_feats[l] is fully overwritten (zero where no RoI contributes): no memset required.
+ * algo 0 picks the deterministic tile-gather kernel when the shape allows (sampling_ratio 1..2,
+ * C % 64 == 0), else the atomic scatter; workspace is only used by the tile-gather path. */
 int dgod_msroi_align_bwd(const dgod_roi_config* cfg /*host*/,
                          const void* grad_out /*device [K,C,PH,PW]*/,
                          const float* rois, int n_rois,
                          const int32_t* roi_img_offsets /*device [batch+1] or NULL*/,
                          void* const* grad_feats /*host array of device ptrs*/,
                          int algo /*0 auto, 1 atomic scatter, 2 tile gather*/,
-                         dgod_stream_t stream);
+                         void* workspace, size_t workspace_bytes, dgod_stream_t stream);
 
 /* ------------------------------------------------------------------ box head post-processing */
 

@@ -253,12 +253,24 @@ def test_multiscale_roi_align(dtype, tol, nhwc):
     scale_ref = np.abs(ref).max()
     np.testing.assert_allclose(got.detach().float().cpu().numpy(), ref, rtol=tol, atol=tol * scale_ref)
     assert pool.scales == scales
-    if dtype == torch.float32:
-        go = torch.randn(ref.shape, generator=synth.gen(9))
-        got.backward(go.to(DEV))
-        grads = O.msroi_align_bwd(go.numpy(), [tuple(f.shape) for f in feats], rois.numpy(), scales, 2, 2, 5)
+    go = torch.randn(ref.shape, generator=synth.gen(9))
+    if dtype == torch.bfloat16:
+        go = go.to(dtype).float()
+    grads = O.msroi_align_bwd(go.numpy(), [tuple(f.shape) for f in feats], rois.numpy(), scales, 2, 2, 5)
+    from dgod_b200 import ops
+    for algo in ((1, 2) if dtype == torch.float32 else (2,)):      # atomic scatter / tile gather
+        ops.BACKWARD_ALGO = algo
+        try:
+            for t in x.values():
+                t.grad = None
+            got.backward(go.to(DEV).to(dtype), retain_graph=True)
+        finally:
+            ops.BACKWARD_ALGO = 0
         for i, gr in enumerate(grads):
-            np.testing.assert_allclose(x[str(i)].grad.cpu().numpy(), gr, rtol=1e-5, atol=1e-5 * max(np.abs(gr).max(), 1e-3))
+            gg = x[str(i)].grad
+            assert gg.dtype == dtype and gg.shape == gr.shape
+            assert gg.is_contiguous(memory_format=torch.channels_last if nhwc else torch.contiguous_format)
+            np.testing.assert_allclose(gg.float().cpu().numpy(), gr, rtol=tol, atol=tol * max(np.abs(gr).max(), 1e-3))
 
 
 def test_roi_align_empty_and_errors():

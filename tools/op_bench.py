@@ -1,0 +1,226 @@
+#!/usr/bin/env python
+"""Op sweep of BASELINE.json configs[3]: per-kernel time and achieved GB/s against the roofline.
+
+    python tools/op_bench.py [--ops roi,nms,match,fcos,rpn,grl] [--iters 20] [--tv] [--json out.json]
+
+Timing: CUDA events on the launching stream, 3 warm-up launches, an L2 flush (a 256 MB write)
+between timed iterations, median over --iters.  Algorithmic bytes follow SURVEY.md §8d.  --tv also
+times the stock torchvision CUDA op on the same inputs (the "existing sm_100 recompile" bar).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import statistics
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from dgod_b200 import ops, synth  # noqa: E402
+from dgod_b200.detector import make_cell_anchors  # noqa: E402
+
+DEV = torch.device("cuda")
+_flush = None
+
+
+def flush_l2():
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=DEV)
+    _flush.fill_(1)
+
+
+def time_op(fn, iters, warmup=3, flush=True):
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush:
+            flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts) * 1e3  # us
+
+
+def peak():
+    f = ROOT / "MEASURED_PEAKS.json"
+    return float(json.loads(f.read_text())["hbm_gbs"]) if f.exists() else 6650.0
+
+
+def row(name, size, us, nbytes, extra=None):
+    gbs = nbytes / 1e3 / us
+    r = {"op": name, "size": size, "us": round(us, 2), "alg_MB": round(nbytes / 1e6, 2), "GB/s": round(gbs, 1),
+         "frac_of_measured_peak": round(gbs / peak(), 4)}
+    if extra:
+        r.update(extra)
+    print(json.dumps(r), flush=True)
+    return r
+
+
+def bench_roi(args, out):
+    B, C, H, W = args.batch, 256, args.height, args.width
+    for dtype in (torch.float32, torch.bfloat16):
+        feats = [f.to(DEV) for f in synth.random_features(B, C, H, W, 0, dtype=dtype)]
+        esz = feats[0].element_size()
+        fbytes = sum(f.numel() for f in feats) * esz
+        scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+        for per in args.rois:
+            boxes = [synth.random_boxes(per, H, W, synth.gen(10 + i)) for i in range(B)]
+            rois = synth.rois_from_boxes(boxes).to(DEV)
+            offs = ops._offsets([per] * B, DEV)
+            K = rois.shape[0]
+            for nhwc in (False, True):
+                fs = [f.contiguous(memory_format=torch.channels_last) if nhwc else f for f in feats]
+                fs = [f.detach().requires_grad_(True) for f in fs]
+                fwd = lambda: ops.multiscale_roi_align(fs, rois, scales, 7, 2, 2, 5, roi_img_offsets=offs)
+                with torch.no_grad():
+                    us = time_op(fwd, args.iters)
+                nb = ops._roi_bytes([f.numel() for f in fs], esz, K, C, 7, 7, 2)
+                tag = f"{'bf16' if dtype == torch.bfloat16 else 'f32'}-{'nhwc' if nhwc else 'nchw'}"
+                out.append(row("msroi_align_fwd", f"B{B} {per}/img {tag}", us, nb))
+                if dtype == torch.float32 or nhwc or True:
+                    o = fwd()
+                    go = torch.randn_like(o)
+                    def bwd():
+                        for f in fs:
+                            f.grad = None
+                        o.backward(go, retain_graph=True)
+                    try:
+                        us = time_op(bwd, args.iters)
+                        nbb = K * C * 49 * esz + 20 * K + fbytes
+                        out.append(row("msroi_align_bwd", f"B{B} {per}/img {tag}", us, nbb))
+                    except RuntimeError as e:
+                        print(json.dumps({"op": "msroi_align_bwd", "size": tag, "error": str(e)[:100]}))
+            if args.tv and dtype == torch.float32:
+                import torchvision
+                pool = torchvision.ops.MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2)
+                x = {str(i): f.detach().requires_grad_(True) for i, f in enumerate(feats)}
+                bl = [b.to(DEV) for b in boxes]
+                fwd_tv = lambda: pool(x, bl, [(H, W)] * B)
+                with torch.no_grad():
+                    us = time_op(fwd_tv, args.iters)
+                out.append(row("torchvision_msroi_fwd", f"B{B} {per}/img f32-nchw", us, nb))
+                o = fwd_tv()
+                go = torch.randn_like(o)
+                def bwd_tv():
+                    for f in x.values():
+                        f.grad = None
+                    o.backward(go, retain_graph=True)
+                us = time_op(bwd_tv, args.iters)
+                out.append(row("torchvision_msroi_bwd", f"B{B} {per}/img f32-nchw", us, K * C * 49 * 4 + 20 * K + fbytes))
+
+
+def bench_nms(args, out):
+    for n in args.nms:
+        g = synth.gen(n)
+        boxes = synth.random_boxes(n, 800, 1333, g).to(DEV)
+        scores = synth.distinct_scores(n, g).to(DEV)
+        idxs = torch.randint(0, 5, (n,), generator=g).to(DEV)
+        keep = ops.batched_nms(boxes, scores, idxs, 0.7)
+        nb = 28 * n + 8 * keep.numel()
+        us = time_op(lambda: ops.nms_segments(boxes, scores, idxs, [n], 0.7), args.iters)
+        out.append(row("batched_nms", f"{n} boxes, 5 groups, thr 0.7", us, nb, {"kept": keep.numel()}))
+        if args.tv:
+            import torchvision
+            us = time_op(lambda: torchvision.ops.batched_nms(boxes, scores, idxs, 0.7), args.iters)
+            out.append(row("torchvision_batched_nms", f"{n} boxes, 5 groups, thr 0.7", us, nb))
+    # the RPN shape: 8 images x 8304 candidates in 5 level groups, one call
+    counts = [8304] * 8
+    n = sum(counts)
+    g = synth.gen(1)
+    boxes = synth.random_boxes(n, 608, 1024, g).to(DEV)
+    scores = synth.distinct_scores(n, g).to(DEV)
+    idxs = torch.randint(0, 5, (n,), generator=g).to(DEV)
+    us = time_op(lambda: ops.nms_segments(boxes, scores, idxs, counts, 0.7, max_out_per_seg=2000), args.iters)
+    out.append(row("batched_nms", "8 images x 8304 boxes, 5 groups (one call)", us, 28 * n + 8 * 8 * 2000))
+
+
+def bench_match(args, out):
+    for (b, m, n, hi, lo, lq, tag) in [(8, 20, 155520, 0.7, 0.3, True, "RPN anchors 608x1024"),
+                                      (8, 20, 268569, 0.7, 0.3, True, "RPN anchors 800x1344"),
+                                      (8, 100, 2000, 0.5, 0.5, False, "RoI heads 100 GT x 2000")]:
+        gts = [synth.random_boxes(m, 608, 1024, synth.gen(i)).to(DEV) for i in range(b)]
+        if n > 10000:
+            boxes = synth.random_boxes(n, 608, 1024, synth.gen(99)).to(DEV)
+            fn = lambda: ops.match_boxes(gts, boxes, hi, lo, lq, want=("labels_f32", "matched_boxes"))
+            nb = b * (16 * m + 8 * n + 4 * n + 16 * n) + 16 * n
+        else:
+            boxes = [synth.random_boxes(n, 608, 1024, synth.gen(50 + i)).to(DEV) for i in range(b)]
+            labels = [torch.randint(1, 9, (m,), generator=synth.gen(i)).to(DEV) for i in range(b)]
+            fn = lambda: ops.match_boxes(gts, boxes, hi, lo, lq, gt_labels=labels, want=("labels_i64", "clamped_idx"))
+            nb = b * (16 * m + 16 * n + 24 * n)
+        out.append(row("iou_match", f"B{b} {m} GT x {n} ({tag})", time_op(fn, args.iters), nb))
+
+
+def bench_fcos(args, out):
+    from oracle import cpu as O  # anchors only (host-side construction of the inputs)
+    import numpy as np
+    for (h, w) in [(800, 1344), (608, 1024)]:
+        anc, npl = [], []
+        for s in (8, 16, 32, 64, 128):
+            gh, gw = -(-h // s), -(-w // s)
+            anc.append(O.grid_anchors(np.array([[-4 * s, -4 * s, 4 * s, 4 * s]], np.float32), gh, gw, s, s))
+            npl.append(gh * gw)
+        a = torch.from_numpy(np.concatenate(anc)).to(DEV)
+        gts = [synth.random_boxes(20, h, w, synth.gen(i)).to(DEV) for i in range(8)]
+        labels = [torch.randint(1, 9, (20,), generator=synth.gen(i)).to(DEV) for i in range(8)]
+        n = a.shape[0]
+        us = time_op(lambda: ops.fcos_assign(a, gts, npl, 1.5), args.iters)
+        out.append(row("fcos_assign", f"B8 {n} locations x 20 GT", us, 8 * (16 * n + 16 * 20 + 8 * n)))
+        us = time_op(lambda: ops.fcos_assign(a, gts, npl, 1.5, gt_labels=labels, num_classes=9), args.iters)
+        out.append(row("fcos_assign+targets", f"B8 {n} locations x 20 GT", us, 8 * (16 * n + 16 * 20 + 8 * n + 8 * n + 16 * n + 36 * n)))
+
+
+def bench_rpn(args, out):
+    cells = [c.tolist() for c in make_cell_anchors(((32,), (64,), (128,), (256,), (512,)), ((0.5, 1.0, 2.0),) * 5)]
+    for (h, w) in [(608, 1024), (800, 1344)]:
+        B = 8
+        g = synth.gen(3)
+        grids = [(-(-h // s), -(-w // s)) for s in (4, 8, 16, 32, 64)]
+        strides = [(h // gh, w // gw) for gh, gw in grids]
+        obj = [torch.randn(B, 3, gh, gw, generator=g).to(DEV) for gh, gw in grids]
+        dl = [(torch.randn(B, 12, gh, gw, generator=g) * 0.2).to(DEV) for gh, gw in grids]
+        sizes = torch.tensor([[h, w]] * B, dtype=torch.float32, device=DEV)
+        A = sum(3 * gh * gw for gh, gw in grids)
+        k = sum(min(2000, 3 * gh * gw) for gh, gw in grids)
+        us = time_op(lambda: ops.rpn_proposals(obj, dl, sizes, strides, cells, 2000, 2000, 0.7), args.iters)
+        out.append(row("rpn_proposals", f"B8 A={A} k={k}", us, B * (4 * A + k * 16 + 2000 * 20)))
+
+
+def bench_grl(args, out):
+    for shape in [(4096, 1024), (8, 256, 152, 256)]:
+        x = torch.randn(*shape, device=DEV)
+        us = time_op(lambda: ops._grl_scale_op(x, 0.1), args.iters)
+        out.append(row("grl_scale", "x".join(map(str, shape)), us, 2 * x.numel() * 4))
+
+
+def main():
+    p = argparse.ArgumentParser()
+    p.add_argument("--ops", default="roi,nms,match,fcos,rpn,grl")
+    p.add_argument("--iters", type=int, default=20)
+    p.add_argument("--batch", type=int, default=8)
+    p.add_argument("--height", type=int, default=608)
+    p.add_argument("--width", type=int, default=1024)
+    p.add_argument("--rois", type=lambda s: [int(x) for x in s.split(",")], default=[512, 2048])
+    p.add_argument("--nms", type=lambda s: [int(x) for x in s.split(",")], default=[1000, 10000, 100000])
+    p.add_argument("--tv", action="store_true")
+    p.add_argument("--json", default="")
+    args = p.parse_args()
+    out = []
+    table = {"roi": bench_roi, "nms": bench_nms, "match": bench_match, "fcos": bench_fcos, "rpn": bench_rpn, "grl": bench_grl}
+    for name in args.ops.split(","):
+        table[name](args, out)
+    if args.json:
+        Path(args.json).write_text(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
