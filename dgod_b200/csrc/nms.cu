@@ -29,91 +29,113 @@ namespace dgod {
 constexpr unsigned long long kKeyMax = ~0ull;
 
 // ---------------------------------------------------------------------------- mask
+// One thread per (row, 64-column chunk): 256 threads = 64 rows x 4 consecutive column chunks,
+// column chunk c = r + 4*blockIdx.y + tid/64, i.e. only chunks on or above the diagonal are ever
+// launched.  Column boxes sit in shared memory and are read as warp broadcasts (a warp = 32 rows of
+// one chunk).  The IoU > threshold test avoids the IEEE division on all but borderline pairs:
+// with t = thr*union, inter > t(1+2^-20) implies fl(inter/union) > thr and inter < t(1-2^-20)
+// implies fl(inter/union) < thr (each fp32 rounding moves a value by at most 2^-24 relative);
+// only pairs in between take the exact quotient.  Non-overlapping pairs exit after 4 min/max.
+constexpr int kMaskChunksPerCta = 4;
+
+__device__ __forceinline__ bool iou_gt_exact(const float4 a, float area_a, const float4 b, float thr,
+                                             bool skip_disjoint) {
+  const float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+  const float h = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+  if (skip_disjoint && (w <= 0.f || h <= 0.f)) return false;   // IoU is 0 (or 0/0): never > thr >= 0
+  const float inter = __fmul_rn(fmaxf(w, 0.f), fmaxf(h, 0.f));
+  const float area_b = box_area_exact(b.x, b.y, b.z, b.w);
+  const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  if (uni > 0.f && thr > 0.f) {
+    const float t = __fmul_rn(thr, uni);
+    if (inter > __fmul_rn(t, 1.00000095367431640625f)) return true;     // 1 + 2^-20
+    if (inter < __fmul_rn(t, 0.99999904632568359375f)) return false;    // 1 - 2^-20
+  }
+  return __fdiv_rn(inter, uni) > thr;
+}
+
 __global__ void __launch_bounds__(256)
 nms_mask_kernel(const float4* __restrict__ sbox, const uint32_t* __restrict__ runkey, int n_pos,
                 float thr, unsigned long long* __restrict__ mask, int row_words) {
-  // column tile, transposed to [bit][chunk] with a one-slot pad: lanes (= chunks) read
-  // consecutive float4s, the staging stores hit distinct bank groups.
-  __shared__ float4 s_box[64][kMaskColSpan + 1];
-  __shared__ uint32_t s_key[64][kMaskColSpan + 1];
-  const int r = blockIdx.x;                                      // row chunk
-  const int cbase = (r / kMaskColSpan + blockIdx.y) * kMaskColSpan;  // first column chunk
+  __shared__ float4 s_box[kMaskChunksPerCta][64];
+  __shared__ uint32_t s_key[kMaskChunksPerCta][64];
+  const int r = blockIdx.x;                                   // row chunk
+  const int c0 = r + kMaskChunksPerCta * blockIdx.y;          // first column chunk of this CTA
   const int row0 = r * 64;
-  const long long col0 = (long long)cbase * 64;
+  const long long col0 = (long long)c0 * 64;
   if (row0 >= n_pos || col0 >= n_pos) return;
-  const int last_row = min(row0 + 63, n_pos - 1);
-  // run keys are non-decreasing: if the first column is already past the last row's run,
-  // no pair of this tile shares a run.  Padding rows (kNoRun) never own pairs.
-  uint32_t rk_last = runkey[last_row];
-  if (rk_last == kNoRun) {
-    // find the last real row of the chunk (rare: only the chunk holding the tail)
-    int p = last_row;
-    while (p >= row0 && runkey[p] == kNoRun) --p;
-    if (p < row0) return;
-    rk_last = runkey[p];
-  }
-  if (runkey[col0] > rk_last) return;
+  // run keys are non-decreasing: if the first column is already past the run of the chunk's last
+  // real row, no pair of this CTA shares a run.  Padding rows (kNoRun) never own pairs.
+  int last = min(row0 + 63, n_pos - 1);
+  uint32_t rk_last = runkey[last];
+  while (rk_last == kNoRun && last > row0) rk_last = runkey[--last];
+  if (rk_last == kNoRun || runkey[col0] > rk_last) return;
 
-  for (int i = threadIdx.x; i < 64 * kMaskColSpan; i += blockDim.x) {
-    long long q = col0 + i;
-    int cc = i >> 6, b = i & 63;
+  {
+    const int cc = threadIdx.x >> 6, b = threadIdx.x & 63;
+    const long long q = col0 + threadIdx.x;
     float4 bx = make_float4(0, 0, 0, 0);
     uint32_t k = kNoRun;
     if (q < n_pos) { bx = sbox[q]; k = runkey[q]; }
-    s_box[b][cc] = bx;
-    s_key[b][cc] = k;
+    s_box[cc][b] = bx;
+    s_key[cc][b] = k;
   }
   __syncthreads();
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = cbase + lane;  // this lane's column chunk
-#pragma unroll 1
-  for (int rr = warp; rr < 64; rr += 8) {
-    const int p = row0 + rr;
-    if (p >= n_pos) break;
-    const uint32_t rk = runkey[p];
-    if (rk == kNoRun) continue;
-    const int w = c - r;
-    if (w < 0 || w >= row_words) continue;
+  const int cc = threadIdx.x >> 6, row = threadIdx.x & 63;
+  const int p = row0 + row;
+  const int w = c0 + cc - r;                                  // word index inside the mask row
+  if (p >= n_pos || w >= row_words) return;
+  const uint32_t rk = runkey[p];
+  if (rk == kNoRun) return;
+  unsigned long long bits = 0ull;
+  const long long qbase = col0 + cc * 64;
+  if (qbase + 63 > p && s_key[cc][0] <= rk && s_key[cc][63] >= rk) {
     const float4 a = sbox[p];
     const float area_a = box_area_exact(a.x, a.y, a.z, a.w);
-    unsigned long long bits = 0ull;
-    const long long qbase = (long long)c * 64;
-    if (qbase + 63 > p && s_key[0][lane] <= rk && s_key[63][lane] >= rk) {
-#pragma unroll 8
-      for (int b = 0; b < 64; ++b) {
-        if (s_key[b][lane] == rk && qbase + b > p) {
-          const float4 bb = s_box[b][lane];
-          float v = iou_exact(a, area_a, bb, box_area_exact(bb.x, bb.y, bb.z, bb.w));
-          if (v > thr) bits |= (1ull << b);
-        }
-      }
+    const bool skip_disjoint = thr >= 0.f;
+#pragma unroll 4
+    for (int b = 0; b < 64; ++b) {
+      if (s_key[cc][b] == rk && qbase + b > p && iou_gt_exact(a, area_a, s_box[cc][b], thr, skip_disjoint))
+        bits |= (1ull << b);
     }
-    mask[(size_t)p * row_words + w] = bits;
   }
+  mask[(size_t)p * row_words + w] = bits;
 }
 
 int launch_nms_mask(const float4* sbox, const uint32_t* runkey, int n_pos, int max_run_len,
                     float thr, unsigned long long* mask, cudaStream_t st) {
   if (n_pos <= 0) return DGOD_OK;
   const int row_words = nms_mask_row_words(max_run_len);
-  // column chunks reachable from a row chunk: [r, r + max_run_len/64 + 1]; the span containing
-  // r starts up to kMaskColSpan-1 chunks before r.
-  const int spans = (max_run_len / 64 + 1 + kMaskColSpan - 1) / kMaskColSpan + 1;
-  dim3 grid(cdiv(n_pos, 64), spans);
+  // a run of length L starting anywhere inside row chunk r reaches column chunk r + L/64 + 1 at most
+  const int groups = (row_words + kMaskChunksPerCta - 1) / kMaskChunksPerCta;
+  dim3 grid(cdiv(n_pos, 64), groups);
   nms_mask_kernel<<<grid, 256, 0, st>>>(sbox, runkey, n_pos, thr, mask, row_words);
   DGOD_LAUNCHED();
   return DGOD_OK;
 }
 
 // ---------------------------------------------------------------------------- scan
-__global__ void __launch_bounds__(256)
+// One CTA per run (the CTA of the chunk in which the run starts).  Per 64-candidate chunk: the
+// chunk's mask rows (all words up to the run's end) are brought into shared memory with cp.async —
+// the next chunk's rows stream in while this one is resolved — thread 0 walks the alive bits of
+// the diagonal word, then every thread ORs the kept rows of its word into the removed-bitmap.
+constexpr int kScanThreads = 256;
+constexpr int kScanMaxWords = 160;   // runs up to ~10k candidates use the staged path
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
+
+__global__ void __launch_bounds__(kScanThreads)
 nms_scan_kernel(const unsigned long long* __restrict__ mask, int row_words,
                 const uint32_t* __restrict__ runkey, const uint8_t* __restrict__ alive, int n_pos,
                 unsigned long long* __restrict__ keepbits, int32_t* __restrict__ compact_pos,
-                int32_t* __restrict__ run_count) {
-  extern __shared__ unsigned long long s_removed[];  // row_words words
-  __shared__ unsigned long long s_diag[64];
+                int32_t* __restrict__ run_count, int staged) {
+  extern __shared__ unsigned long long s_dyn[];     // removed[row_words] | rows[2][64][row_words] (staged)
+  unsigned long long* s_removed = s_dyn;
+  unsigned long long* s_rows = s_dyn + row_words;
   __shared__ uint32_t s_ballot[2];
   __shared__ unsigned long long s_kept;
   const int c = blockIdx.x, tid = threadIdx.x;
@@ -144,28 +166,42 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, int row_words,
     }
     const int e = lo;
     const int cs = s >> 6, ce = (e - 1) >> 6;
-    __syncthreads();  // previous run done with s_removed
+    __syncthreads();  // previous run done with the shared buffers
     for (int w = tid; w <= ce - cs && w < row_words; w += blockDim.x) s_removed[w] = 0ull;
-    __syncthreads();
+    auto stage = [&](int cc, int buf) {      // rows of chunk cc, words 0..ce-cc, into rows[buf]
+      const int nw = ce - cc + 1;
+      unsigned long long* dst = s_rows + (size_t)buf * 64 * row_words;
+      for (int i = tid; i < 64 * nw; i += blockDim.x) {
+        const int row = i / nw, w = i - row * nw;
+        const int p = cc * 64 + row;
+        if (p >= s && p < e) cp_async8(dst + row * row_words + w, mask + (size_t)p * row_words + w);
+      }
+      asm volatile("cp.async.commit_group;\n" ::);
+    };
+    if (staged) stage(cs, 0);
     int count = 0;
     for (int cc = cs; cc <= ce; ++cc) {
+      const int buf = (cc - cs) & 1;
+      const unsigned long long* rows = s_rows + (size_t)buf * 64 * row_words;
+      bool in = false;
       if (tid < 64) {
         const int p = cc * 64 + tid;
-        bool in = p >= s && p < e && (!alive || alive[p]);
-        s_diag[tid] = in ? mask[(size_t)p * row_words] : 0ull;
+        in = p >= s && p < e && (!alive || alive[p]);
         uint32_t bal = __ballot_sync(0xffffffffu, in);
         if ((tid & 31) == 0) s_ballot[tid >> 5] = bal;
       }
-      __syncthreads();
+      if (staged) asm volatile("cp.async.wait_group 0;\n" ::);
+      __syncthreads();                                   // rows of chunk cc landed; removed[] is current
+      if (staged && cc < ce) stage(cc + 1, buf ^ 1);     // overlaps with the resolve below
       if (tid == 0) {
         unsigned long long al = (((unsigned long long)s_ballot[1] << 32) | s_ballot[0]) & ~s_removed[cc - cs];
         unsigned long long kept = 0ull;
-#pragma unroll 8
-        for (int b = 0; b < 64; ++b) {
-          if ((al >> b) & 1ull) {
-            kept |= (1ull << b);
-            al &= ~s_diag[b];
-          }
+        while (al) {
+          const int b = __ffsll((long long)al) - 1;
+          kept |= (1ull << b);
+          const unsigned long long d = staged ? rows[b * row_words] : mask[(size_t)(cc * 64 + b) * row_words];
+          al &= ~d;
+          al &= ~(1ull << b);
         }
         s_kept = kept;
       }
@@ -173,10 +209,25 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, int row_words,
       const unsigned long long kept = s_kept;
       for (int w = tid + 1; cc + w <= ce; w += blockDim.x) {
         unsigned long long acc = 0ull, kk = kept;
-        while (kk) {
-          const int b = __ffsll((long long)kk) - 1;
-          kk &= kk - 1;
-          acc |= mask[(size_t)(cc * 64 + b) * row_words + w];
+        if (staged) {
+          while (kk) {
+            const int b = __ffsll((long long)kk) - 1;
+            kk &= kk - 1;
+            acc |= rows[b * row_words + w];
+          }
+        } else {
+          while (kk) {   // four independent loads in flight per step
+            unsigned long long v[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (kk) {
+                const int b = __ffsll((long long)kk) - 1;
+                kk &= kk - 1;
+                v[u] = mask[(size_t)(cc * 64 + b) * row_words + w];
+              }
+            }
+            acc |= (v[0] | v[1]) | (v[2] | v[3]);
+          }
         }
         s_removed[cc - cs + w] |= acc;
       }
@@ -186,7 +237,6 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, int row_words,
       }
       if (tid == 0 && kept) atomicOr(&keepbits[cc], kept);
       count += __popcll(kept);
-      __syncthreads();
     }
     if (run_count && tid == 0) run_count[rk] = count;
   }
@@ -197,13 +247,15 @@ int launch_nms_scan(const unsigned long long* mask, const uint32_t* runkey, cons
                     int32_t* compact_pos, int32_t* run_count, cudaStream_t st) {
   if (n_pos <= 0) return DGOD_OK;
   const int row_words = nms_mask_row_words(max_run_len);
-  const size_t smem = (size_t)row_words * sizeof(unsigned long long);
-  if (smem > 48 * 1024) {
-    DGOD_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
+  const int staged = row_words <= kScanMaxWords;
+  const size_t smem = (size_t)row_words * sizeof(unsigned long long) * (staged ? 1 + 2 * 64 : 1);
+  static size_t attr_smem = 0;
+  if (smem > 48 * 1024 && smem > attr_smem) {
+    DGOD_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
   }
-  nms_scan_kernel<<<cdiv(n_pos, 64), 256, smem, st>>>(mask, row_words, runkey, alive, n_pos,
-                                                     keepbits, compact_pos, run_count);
+  nms_scan_kernel<<<cdiv(n_pos, 64), kScanThreads, smem, st>>>(mask, row_words, runkey, alive, n_pos, keepbits,
+                                                              compact_pos, run_count, staged);
   DGOD_LAUNCHED();
   return DGOD_OK;
 }

@@ -8,7 +8,6 @@
 namespace dgod {
 
 constexpr uint32_t kNoRun = 0xffffffffu;  // run key of padding / masked-out positions
-constexpr int kMaskColSpan = 32;          // 64-column chunks handled per mask CTA
 
 // Words per mask row: a row covers column chunks [p/64, p/64 + words).
 static inline int nms_mask_row_words(int max_run_len) { return max_run_len / 64 + 2; }

@@ -164,6 +164,8 @@ int msroi_bwd_fast(const dgod_roi_config* cfg, const RoiDev& g, const void* grad
                    const float* rois, int n_rois, const int32_t* roi_img_offsets, void* workspace,
                    size_t workspace_bytes, cudaStream_t st, int* handled);
 size_t msroi_bwd_workspace(int n_rois);
+int msroi_bwd_red(const dgod_roi_config* cfg, const RoiDev& g, const void* grad_out, const float* rois,
+                  int n_rois, cudaStream_t st, int* handled);
 
 }  // namespace dgod
 
@@ -228,6 +230,11 @@ extern "C" int dgod_msroi_align_bwd(const dgod_roi_config* cfg, const void* grad
     DGOD_CUDA(cudaMemsetAsync(g.gfeat[l], 0, (size_t)g.B * g.C * g.H[l] * g.W[l] * esz, st));
   if (n_rois == 0) return DGOD_OK;
   DGOD_REQUIRE(cfg->dtype == DGOD_F32, "roi_align: the atomic backward supports fp32 gradients only");
+  {
+    int handled = 0;
+    rc = msroi_bwd_red(cfg, g, grad_out, rois, n_rois, st, &handled);   // NHWC: 16-byte vector reductions
+    if (rc || handled) return rc;
+  }
   if (g.channels_last) msroi_bwd_atomic_kernel<true><<<n_rois, kRoiThreads, 0, st>>>(g, (const float*)grad_out, rois, n_rois);
   else msroi_bwd_atomic_kernel<false><<<n_rois, kRoiThreads, 0, st>>>(g, (const float*)grad_out, rois, n_rois);
   DGOD_LAUNCHED();

@@ -175,6 +175,75 @@ msroi_fwd_nhwc_kernel(const RoiDev g, const float* __restrict__ rois, int n_rois
 }
 
 // ------------------------------------------------------------------------------------------------
+// Backward, NHWC, vector reductions (algo 1 on channels_last gradients).  Mirror image of the
+// forward: one CTA per RoI, lanes = channels, the same per-bin (offset, weight) table.  The RoI's
+// [C][49] gradient block is staged through shared memory (contiguous 128-bit reads), then every
+// tap is ONE 16-byte `red.global.add.v4.f32` per lane — 512 contiguous bytes per warp, so the L2
+// atomic units see full sectors instead of the 4-byte scatter of the reference kernel.
+// grad_in must be zero-filled first (done by the launcher).  Accumulation order across RoIs is
+// not deterministic (like the reference CUDA kernel); the tile-gather kernel below is.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int SR>
+__global__ void __launch_bounds__(256)
+msroi_bwd_red_nhwc_kernel(const RoiDev g, const float* __restrict__ grad_out, const float* __restrict__ rois,
+                          int n_rois) {
+  constexpr int NTAP = 4 * SR * SR;
+  constexpr int VEC = 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ AxisTab ty, tx;
+  __shared__ RoiGeom s_geo;
+  const int k = blockIdx.x;
+  if (threadIdx.x == 0) s_geo = roi_geometry(g, rois + (size_t)k * 5);
+  __syncthreads();
+  const RoiGeom r = s_geo;
+  if (r.batch < 0 || r.batch >= g.B) return;
+  const int PH = g.PH, PW = g.PW, C = g.C;
+  const int nbin = PH * PW;
+  int2* s_tab = reinterpret_cast<int2*>(smem_raw);                                        // [nbin][NTAP]
+  float* s_g = reinterpret_cast<float*>(smem_raw + (size_t)nbin * NTAP * sizeof(int2));   // [C][nbin]
+  const int ny = PH * SR, nx = PW * SR;
+  if (threadIdx.x < ny) fill_axis(ty, threadIdx.x, r.start_h, r.bin_h, SR, r.H, r.W * C);
+  else if (threadIdx.x >= 32 && threadIdx.x < 32 + nx) fill_axis(tx, threadIdx.x - 32, r.start_w, r.bin_w, SR, r.W, C);
+  {
+    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(grad_out + (size_t)k * C * nbin);
+    uint4* dst = reinterpret_cast<uint4*>(s_g);
+    for (int i = threadIdx.x; i < C * nbin / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nbin * NTAP; e += blockDim.x) {
+    const int bin = e / NTAP, tap = e - bin * NTAP;
+    const int ph = bin / PW, pw = bin - ph * PW;
+    const int smp = tap >> 2, j = tap & 3;
+    const int sy = ph * SR + smp / SR, sx = pw * SR + smp % SR;
+    const int yo = (j & 2) ? ty.hi[sy] : ty.lo[sy];
+    const int xo = (j & 1) ? tx.hi[sx] : tx.lo[sx];
+    const float wy = (j & 2) ? ty.l[sy] : ty.h[sy];
+    const float wx = (j & 1) ? tx.l[sx] : tx.h[sx];
+    s_tab[e] = make_int2(yo + xo, __float_as_int(__fmul_rn(wy, wx)));
+  }
+  __syncthreads();
+  const int c0 = threadIdx.x * VEC;
+  float* __restrict__ img = reinterpret_cast<float*>(g.gfeat[r.level]) + (size_t)r.batch * r.H * r.W * C + c0;
+  const float inv_cnt = 1.f / (float)(SR * SR);   // SR*SR is a power of two: (g*w)/count == (g*w)*inv exactly
+  for (int bin = 0; bin < nbin; ++bin) {
+    float gv[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) gv[v] = s_g[(c0 + v) * nbin + bin];
+#pragma unroll
+    for (int t = 0; t < NTAP; ++t) {
+      const int2 e = s_tab[bin * NTAP + t];
+      const float w = __int_as_float(e.y);
+      if (w != 0.f)   // out-of-range samples (and exactly-zero weights) add nothing
+        red_add_v4(img + e.x, __fmul_rn(__fmul_rn(gv[0], w), inv_cnt), __fmul_rn(__fmul_rn(gv[1], w), inv_cnt),
+                   __fmul_rn(__fmul_rn(gv[2], w), inv_cnt), __fmul_rn(__fmul_rn(gv[3], w), inv_cnt));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Backward, tile gather.
 constexpr int kTile = 16;          // tile is kTile x kTile pixels
 constexpr int kBwdThreads = 256;   // 8 warps; warp w owns pixels w, w+8, ... of the tile
@@ -445,6 +514,29 @@ int msroi_fwd_fast(const dgod_roi_config* cfg, const RoiDev& g, const float* roi
   }
   *handled = 1;
   return rc;
+}
+
+int msroi_bwd_red(const dgod_roi_config* cfg, const RoiDev& g, const void* grad_out, const float* rois,
+                  int n_rois, cudaStream_t st, int* handled) {
+  *handled = 0;
+  if (!g.channels_last || cfg->dtype != DGOD_F32 || !fast_shape_ok(cfg) || g.C % 4 != 0 || g.C / 4 > 256 ||
+      g.C / 4 < 32 + kMaxS || ((size_t)g.C * g.PH * g.PW) % 4 != 0 || ((uintptr_t)grad_out & 15))
+    return DGOD_OK;
+  for (int l = 0; l < g.n_levels; ++l)
+    if ((uintptr_t)g.gfeat[l] & 15) return DGOD_OK;
+  const int sr = g.sr;
+  const size_t smem = (size_t)g.C * g.PH * g.PW * sizeof(float) + (size_t)g.PH * g.PW * 4 * sr * sr * sizeof(int2);
+  static size_t attr_smem[3] = {0, 0, 0};
+  if (smem > 48 * 1024 && smem > attr_smem[sr]) {
+    if (sr == 2) DGOD_CUDA(cudaFuncSetAttribute(msroi_bwd_red_nhwc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else DGOD_CUDA(cudaFuncSetAttribute(msroi_bwd_red_nhwc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[sr] = smem;
+  }
+  if (sr == 2) msroi_bwd_red_nhwc_kernel<2><<<n_rois, g.C / 4, smem, st>>>(g, (const float*)grad_out, rois, n_rois);
+  else msroi_bwd_red_nhwc_kernel<1><<<n_rois, g.C / 4, smem, st>>>(g, (const float*)grad_out, rois, n_rois);
+  DGOD_LAUNCHED();
+  *handled = 1;
+  return DGOD_OK;
 }
 
 size_t msroi_bwd_workspace(int n_rois) { return align_up((size_t)(n_rois > 0 ? n_rois : 1) * sizeof(RoiPrep), 256); }

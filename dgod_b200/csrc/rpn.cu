@@ -20,6 +20,7 @@
 namespace dgod {
 
 constexpr int kTopkThreads = 1024;
+constexpr int kSelUnroll = 8;          // independent loads in flight per thread in the selection passes
 
 struct RpnDev {
   const float* obj[DGOD_MAX_LEVELS];
@@ -47,13 +48,24 @@ __device__ void radix_select(KeyFn keyfn, int n, int k, uint32_t* s_hist, uint32
   for (int shift = 24; shift >= 0; shift -= 8) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0u;
     __syncthreads();
-    for (int base = 0; base < n; base += blockDim.x) {
-      const int m = base + threadIdx.x;
-      uint32_t key = 0u;
-      bool part = m < n && keyfn(m, key) && ((key & pmask) == prefix);
-      const uint32_t digit = part ? ((key >> shift) & 255u) : 256u;
-      const uint32_t peers = __match_any_sync(0xffffffffu, digit);
-      if (part && lane == __ffs(peers) - 1) atomicAdd(&s_hist[digit], (uint32_t)__popc(peers));
+    for (int base = 0; base < n; base += kSelUnroll * blockDim.x) {
+      // issue the loads of kSelUnroll elements before the first histogram update (the update's
+      // warp-wide match would otherwise serialise one global-memory latency per element)
+      uint32_t keys[kSelUnroll];
+      bool parts[kSelUnroll];
+#pragma unroll
+      for (int u = 0; u < kSelUnroll; ++u) {
+        const int m = base + u * blockDim.x + threadIdx.x;
+        keys[u] = 0u;
+        parts[u] = m < n && keyfn(m, keys[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < kSelUnroll; ++u) {
+        const bool part = parts[u] && ((keys[u] & pmask) == prefix);
+        const uint32_t digit = part ? ((keys[u] >> shift) & 255u) : 256u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        if (part && lane == __ffs(peers) - 1) atomicAdd(&s_hist[digit], (uint32_t)__popc(peers));
+      }
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -161,16 +173,25 @@ rpn_topk_decode_kernel(const RpnDev g, const float* __restrict__ proposals_flat,
       int a_, b_;
       radix_select(key_tie, n, need, s_hist, s_bc, T2, a_, b_);
     }
-    for (int base = 0; base < n; base += blockDim.x) {
-      const int m = base + threadIdx.x;
-      uint32_t key = 0u, r = 0u;
-      bool sel = false;
-      if (m < n) {
-        key_logit(m, key);
-        r = ref_index(m);
-        sel = key < T || (key == T && r <= T2);
+    for (int base = 0; base < n; base += kSelUnroll * blockDim.x) {
+      uint32_t keys[kSelUnroll];
+#pragma unroll
+      for (int u = 0; u < kSelUnroll; ++u) {
+        const int m = base + u * blockDim.x + threadIdx.x;
+        keys[u] = 0xffffffffu;
+        if (m < n) key_logit(m, keys[u]);
       }
-      append_selected(sel, ((unsigned long long)key << 32) | r, s_sel, &s_count);
+#pragma unroll
+      for (int u = 0; u < kSelUnroll; ++u) {
+        const int m = base + u * blockDim.x + threadIdx.x;
+        uint32_t r = 0u;
+        bool sel = false;
+        if (m < n) {
+          r = ref_index(m);
+          sel = keys[u] < T || (keys[u] == T && r <= T2);
+        }
+        append_selected(sel, ((unsigned long long)keys[u] << 32) | r, s_sel, &s_count);
+      }
     }
   }
   __syncthreads();

@@ -452,7 +452,9 @@ def _(grad, rois, roi_img_offsets, shapes, channels_last, scales, pooled_h, pool
     return [grad.new_empty((b, c, shapes[2 + 2 * l], shapes[3 + 2 * l])) for l in range(len(scales))]
 
 
-BACKWARD_ALGO = 0  # 0 auto, 1 atomic scatter, 2 tile gather (dgod_msroi_align_bwd)
+import os as _os
+
+BACKWARD_ALGO = int(_os.environ.get("DGOD_BWD_ALGO", "0"))  # 0 auto, 1 atomic / vector-RED scatter, 2 tile gather
 
 
 def _msroi_setup(ctx, inputs, output):
