@@ -56,9 +56,11 @@ __device__ __forceinline__ bool iou_gt_exact(const float4 a, float area_a, const
 
 __global__ void __launch_bounds__(256)
 nms_mask_kernel(const float4* __restrict__ sbox, const uint32_t* __restrict__ runkey, int n_pos,
-                float thr, unsigned long long* __restrict__ mask, int row_words) {
+                float thr, unsigned long long* __restrict__ mask, int row_words,
+                unsigned long long* __restrict__ diag_cols) {
   __shared__ float4 s_box[kMaskChunksPerCta][64];
   __shared__ uint32_t s_key[kMaskChunksPerCta][64];
+  __shared__ uint32_t s_colbits[64][2];
   const int r = blockIdx.x;                                   // row chunk
   const int c0 = r + kMaskChunksPerCta * blockIdx.y;          // first column chunk of this CTA
   const int row0 = r * 64;
@@ -69,7 +71,10 @@ nms_mask_kernel(const float4* __restrict__ sbox, const uint32_t* __restrict__ ru
   int last = min(row0 + 63, n_pos - 1);
   uint32_t rk_last = runkey[last];
   while (rk_last == kNoRun && last > row0) rk_last = runkey[--last];
-  if (rk_last == kNoRun || runkey[col0] > rk_last) return;
+  if (rk_last == kNoRun || runkey[col0] > rk_last) {
+    if (blockIdx.y == 0 && threadIdx.x < 64 && row0 + (int)threadIdx.x < n_pos) diag_cols[row0 + threadIdx.x] = 0ull;
+    return;
+  }
 
   {
     const int cc = threadIdx.x >> 6, b = threadIdx.x & 63;
@@ -85,12 +90,13 @@ nms_mask_kernel(const float4* __restrict__ sbox, const uint32_t* __restrict__ ru
   const int cc = threadIdx.x >> 6, row = threadIdx.x & 63;
   const int p = row0 + row;
   const int w = c0 + cc - r;                                  // word index inside the mask row
-  if (p >= n_pos || w >= row_words) return;
-  const uint32_t rk = runkey[p];
-  if (rk == kNoRun) return;
+  const bool diag = blockIdx.y == 0 && cc == 0;               // warps 0-1 of the first CTA: the diagonal tile
+  const bool active = p < n_pos && w < row_words;
+  const uint32_t rk = active ? runkey[p] : kNoRun;
+  if (!diag && rk == kNoRun) return;
   unsigned long long bits = 0ull;
   const long long qbase = col0 + cc * 64;
-  if (qbase + 63 > p && s_key[cc][0] <= rk && s_key[cc][63] >= rk) {
+  if (rk != kNoRun && qbase + 63 > p && s_key[cc][0] <= rk && s_key[cc][63] >= rk) {
     const float4 a = sbox[p];
     const float area_a = box_area_exact(a.x, a.y, a.z, a.w);
     const bool skip_disjoint = thr >= 0.f;
@@ -100,17 +106,29 @@ nms_mask_kernel(const float4* __restrict__ sbox, const uint32_t* __restrict__ ru
         bits |= (1ull << b);
     }
   }
-  mask[(size_t)p * row_words + w] = bits;
+  if (rk != kNoRun) mask[(size_t)p * row_words + w] = bits;
+  if (diag) {
+    // transpose of the diagonal 64x64 block: diag_cols[q] = rows of the chunk that suppress q
+    // (what the scan's fixpoint resolve consumes); rows 0-31 ballot in warp 0, rows 32-63 in warp 1
+#pragma unroll 8
+    for (int b = 0; b < 64; ++b) {
+      const uint32_t bal = __ballot_sync(0xffffffffu, (bits >> b) & 1ull);
+      if ((threadIdx.x & 31) == 0) s_colbits[b][threadIdx.x >> 5] = bal;
+    }
+    // the two warps meet on a named barrier (the other six warps may already have left)
+    asm volatile("bar.sync 1, 64;\n" ::);
+    if (p < n_pos) diag_cols[p] = ((unsigned long long)s_colbits[row][1] << 32) | s_colbits[row][0];
+  }
 }
 
 int launch_nms_mask(const float4* sbox, const uint32_t* runkey, int n_pos, int max_run_len,
-                    float thr, unsigned long long* mask, cudaStream_t st) {
+                    float thr, unsigned long long* mask, unsigned long long* diag_cols, cudaStream_t st) {
   if (n_pos <= 0) return DGOD_OK;
   const int row_words = nms_mask_row_words(max_run_len);
   // a run of length L starting anywhere inside row chunk r reaches column chunk r + L/64 + 1 at most
   const int groups = (row_words + kMaskChunksPerCta - 1) / kMaskChunksPerCta;
   dim3 grid(cdiv(n_pos, 64), groups);
-  nms_mask_kernel<<<grid, 256, 0, st>>>(sbox, runkey, n_pos, thr, mask, row_words);
+  nms_mask_kernel<<<grid, 256, 0, st>>>(sbox, runkey, n_pos, thr, mask, row_words, diag_cols);
   DGOD_LAUNCHED();
   return DGOD_OK;
 }
@@ -129,8 +147,8 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
 }
 
 __global__ void __launch_bounds__(kScanThreads)
-nms_scan_kernel(const unsigned long long* __restrict__ mask, int row_words,
-                const uint32_t* __restrict__ runkey, const uint8_t* __restrict__ alive, int n_pos,
+nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long long* __restrict__ diag_cols,
+                int row_words, const uint32_t* __restrict__ runkey, const uint8_t* __restrict__ alive, int n_pos,
                 unsigned long long* __restrict__ keepbits, int32_t* __restrict__ compact_pos,
                 int32_t* __restrict__ run_count, int staged) {
   extern __shared__ unsigned long long s_dyn[];     // removed[row_words] | rows[2][64][row_words] (staged)
@@ -193,29 +211,48 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, int row_words,
       if (staged) asm volatile("cp.async.wait_group 0;\n" ::);
       __syncthreads();                                   // rows of chunk cc landed; removed[] is current
       if (staged && cc < ce) stage(cc + 1, buf ^ 1);     // overlaps with the resolve below
-      if (tid == 0) {
-        unsigned long long al = (((unsigned long long)s_ballot[1] << 32) | s_ballot[0]) & ~s_removed[cc - cs];
-        unsigned long long kept = 0ull;
-        while (al) {
-          const int b = __ffsll((long long)al) - 1;
-          kept |= (1ull << b);
-          const unsigned long long d = staged ? rows[b * row_words] : mask[(size_t)(cc * 64 + b) * row_words];
-          al &= ~d;
-          al &= ~(1ull << b);
+      if (tid < 32) {
+        // Greedy keep set of the chunk as the fixpoint of
+        //   K[b] = alive[b] and no a < b with K[a] and D[a][b]
+        // iterated from K = alive: entry b is final after b+1 sweeps at the latest, in practice
+        // after (longest suppression chain + 1) sweeps; each sweep is two ballots.
+        const unsigned long long al = (((unsigned long long)s_ballot[1] << 32) | s_ballot[0]) & ~s_removed[cc - cs];
+        const int q0 = cc * 64 + tid, q1 = q0 + 32;
+        const unsigned long long col0 = q0 < n_pos ? diag_cols[q0] : 0ull;   // only rows a < b of the same run
+        const unsigned long long col1 = q1 < n_pos ? diag_cols[q1] : 0ull;
+        unsigned long long K = al;
+        while (true) {
+          const bool k0 = ((al >> tid) & 1ull) && ((col0 & K) == 0ull);
+          const bool k1 = ((al >> (tid + 32)) & 1ull) && ((col1 & K) == 0ull);
+          const unsigned long long Kn = ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32) | __ballot_sync(0xffffffffu, k0);
+          if (Kn == K) break;
+          K = Kn;
         }
-        s_kept = kept;
+        if (tid == 0) s_kept = K;
       }
       __syncthreads();
       const unsigned long long kept = s_kept;
-      for (int w = tid + 1; cc + w <= ce; w += blockDim.x) {
-        unsigned long long acc = 0ull, kk = kept;
-        if (staged) {
-          while (kk) {
-            const int b = __ffsll((long long)kk) - 1;
-            kk &= kk - 1;
-            acc |= rows[b * row_words + w];
+      if (staged) {
+        // 8 threads per word: each ORs every 8th kept row, then a 3-step shuffle OR
+        for (int w0 = 1; cc + w0 <= ce; w0 += kScanThreads / 8) {
+          const int w = w0 + (tid >> 3), part = tid & 7;
+          unsigned long long acc = 0ull;
+          if (cc + w <= ce) {
+            unsigned long long kk = kept & (0x0101010101010101ull << part);
+            while (kk) {
+              const int b = __ffsll((long long)kk) - 1;
+              kk &= kk - 1;
+              acc |= rows[b * row_words + w];
+            }
           }
-        } else {
+          acc |= __shfl_xor_sync(0xffffffffu, acc, 1);
+          acc |= __shfl_xor_sync(0xffffffffu, acc, 2);
+          acc |= __shfl_xor_sync(0xffffffffu, acc, 4);
+          if (part == 0 && cc + w <= ce) s_removed[cc - cs + w] |= acc;
+        }
+      } else {
+        for (int w = tid + 1; cc + w <= ce; w += blockDim.x) {
+          unsigned long long acc = 0ull, kk = kept;
           while (kk) {   // four independent loads in flight per step
             unsigned long long v[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
@@ -228,8 +265,8 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, int row_words,
             }
             acc |= (v[0] | v[1]) | (v[2] | v[3]);
           }
+          s_removed[cc - cs + w] |= acc;
         }
-        s_removed[cc - cs + w] |= acc;
       }
       if (tid < 64 && ((kept >> tid) & 1ull) && compact_pos) {
         const int j = count + __popcll(kept & ((1ull << tid) - 1ull));
@@ -242,8 +279,8 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, int row_words,
   }
 }
 
-int launch_nms_scan(const unsigned long long* mask, const uint32_t* runkey, const uint8_t* alive,
-                    int n_pos, int max_run_len, unsigned long long* keepbits,
+int launch_nms_scan(const unsigned long long* mask, const unsigned long long* diag_cols, const uint32_t* runkey,
+                    const uint8_t* alive, int n_pos, int max_run_len, unsigned long long* keepbits,
                     int32_t* compact_pos, int32_t* run_count, cudaStream_t st) {
   if (n_pos <= 0) return DGOD_OK;
   const int row_words = nms_mask_row_words(max_run_len);
@@ -254,7 +291,7 @@ int launch_nms_scan(const unsigned long long* mask, const uint32_t* runkey, cons
     DGOD_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  nms_scan_kernel<<<cdiv(n_pos, 64), kScanThreads, smem, st>>>(mask, row_words, runkey, alive, n_pos, keepbits,
+  nms_scan_kernel<<<cdiv(n_pos, 64), kScanThreads, smem, st>>>(mask, diag_cols, row_words, runkey, alive, n_pos, keepbits,
                                                               compact_pos, run_count, staged);
   DGOD_LAUNCHED();
   return DGOD_OK;
@@ -359,6 +396,7 @@ struct NmsBuffers {
   uint32_t* runkey;
   unsigned long long* mask;
   unsigned long long* keepbits;
+  unsigned long long* diag_cols;
   uint32_t* seg_max;
 };
 
@@ -369,6 +407,7 @@ static size_t carve(Workspace& ws, NmsBuffers& b, int n_total, int n_seg, int ma
   b.sbox = ws.take<float4>(P);
   b.runkey = ws.take<uint32_t>(P);
   b.keepbits = ws.take<unsigned long long>(P / 64 + 1);
+  b.diag_cols = ws.take<unsigned long long>(P);
   b.seg_max = ws.take<uint32_t>(n_seg > 0 ? n_seg : 1);
   b.mask = ws.take<unsigned long long>((size_t)(n_total > 0 ? n_total : 1) * nms_mask_row_words(max_seg_len));
   return ws.used;
@@ -423,9 +462,9 @@ extern "C" int dgod_nms_batched(const float* boxes, const float* scores, const i
                                                   offset_mode, b.sbox, b.runkey);
   DGOD_LAUNCHED();
   // positions >= n_total are padding (kNoRun) and sort to the tail: only n_total positions matter
-  rc = launch_nms_mask(b.sbox, b.runkey, n_total, max_seg_len, thr, b.mask, st);
+  rc = launch_nms_mask(b.sbox, b.runkey, n_total, max_seg_len, thr, b.mask, b.diag_cols, st);
   if (rc) return rc;
-  rc = launch_nms_scan(b.mask, b.runkey, nullptr, n_total, max_seg_len, b.keepbits, nullptr, nullptr, st);
+  rc = launch_nms_scan(b.mask, b.diag_cols, b.runkey, nullptr, n_total, max_seg_len, b.keepbits, nullptr, nullptr, st);
   if (rc) return rc;
   nms_rekey_kernel<<<cdiv(P, 256), 256, 0, st>>>(b.keys, b.keepbits, P);
   DGOD_LAUNCHED();

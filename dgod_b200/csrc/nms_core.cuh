@@ -14,15 +14,18 @@ static inline int nms_mask_row_words(int max_run_len) { return max_run_len / 64 
 
 // mask[p*row_words + w] bit b  <=>  position q = (p/64 + w)*64 + b is in p's run, q > p, and
 // IoU(p,q) > threshold.
+// diag_cols[q] (one word per position) = transpose of the diagonal block: the rows of q's own
+// 64-chunk that suppress q.
 int launch_nms_mask(const float4* sbox, const uint32_t* runkey, int n_pos, int max_run_len,
-                    float thr_rounded_down, unsigned long long* mask, cudaStream_t st);
+                    float thr_rounded_down, unsigned long long* mask, unsigned long long* diag_cols,
+                    cudaStream_t st);
 
 // Sequential greedy pass per run.  alive (optional, per position) = 0 removes a candidate
 // before NMS.  keepbits must be zeroed by the caller.  compact_pos (optional): kept positions
 // of a run written contiguously from the run's first position; run_count (optional) is indexed
 // by run key.
-int launch_nms_scan(const unsigned long long* mask, const uint32_t* runkey, const uint8_t* alive,
-                    int n_pos, int max_run_len, unsigned long long* keepbits,
+int launch_nms_scan(const unsigned long long* mask, const unsigned long long* diag_cols, const uint32_t* runkey,
+                    const uint8_t* alive, int n_pos, int max_run_len, unsigned long long* keepbits,
                     int32_t* compact_pos, int32_t* run_count, cudaStream_t st);
 
 }  // namespace dgod

@@ -16,10 +16,14 @@
 // Where torch.topk leaves the order of *equal logits* implementation-defined, this kernel uses
 // ascending anchor index ("ties").
 #include "nms_core.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace dgod {
 
 constexpr int kTopkThreads = 1024;
+constexpr int kTopkCluster = 8;        // CTAs (one cluster) sharing the objectness of one (level, image)
 constexpr int kSelUnroll = 8;          // independent loads in flight per thread in the selection passes
 
 struct RpnDev {
@@ -36,19 +40,30 @@ struct RpnDev {
   float cell[DGOD_MAX_LEVELS][DGOD_MAX_CELL_ANCHORS][4];
 };
 
-// ---- CTA-wide radix select: threshold of the k smallest 32-bit keys --------------------------
-// keyfn(m, key) -> bool participates.  On return (all threads): T = k-th smallest key,
-// n_lt = #keys < T, n_eq = #keys == T.  s_hist: 256 words, s_bc: 4 words of shared scratch.
+// ---- cluster-wide radix select: threshold of the k smallest 32-bit keys -----------------------
+// The kTopkCluster CTAs of a cluster each own the slice [m0, m1) of the level's elements.  Per
+// 8-bit digit: local histogram in shared memory, cluster barrier, rank 0 adds the eight histograms
+// through distributed shared memory and picks the digit, second cluster barrier, every CTA reads
+// the decision from rank 0.  keyfn(m, key) -> bool participates.  On return (all threads of all
+// CTAs): T = k-th smallest key, n_lt = #keys < T, n_eq = #keys == T.
+struct SelShared {
+  uint32_t hist[256];
+  uint32_t total[256];   // rank 0 only
+  uint32_t bc[4];        // rank 0 only: chosen digit, #keys below it, #keys in it
+};
+
 template <typename KeyFn>
-__device__ void radix_select(KeyFn keyfn, int n, int k, uint32_t* s_hist, uint32_t* s_bc,
+__device__ void radix_select(KeyFn keyfn, int m0, int m1, int k, SelShared* sh, cg::cluster_group& cluster,
                              uint32_t& T, int& n_lt, int& n_eq) {
   uint32_t prefix = 0u, pmask = 0u;
   int remaining = k, lt_total = 0, eq = 0;
   const int lane = threadIdx.x & 31;
+  const unsigned rank = cluster.block_rank();
+  SelShared* sh0 = cluster.map_shared_rank(sh, 0);
   for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0u;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh->hist[i] = 0u;
     __syncthreads();
-    for (int base = 0; base < n; base += kSelUnroll * blockDim.x) {
+    for (int base = m0; base < m1; base += kSelUnroll * blockDim.x) {
       // issue the loads of kSelUnroll elements before the first histogram update (the update's
       // warp-wide match would otherwise serialise one global-memory latency per element)
       uint32_t keys[kSelUnroll];
@@ -57,53 +72,63 @@ __device__ void radix_select(KeyFn keyfn, int n, int k, uint32_t* s_hist, uint32
       for (int u = 0; u < kSelUnroll; ++u) {
         const int m = base + u * blockDim.x + threadIdx.x;
         keys[u] = 0u;
-        parts[u] = m < n && keyfn(m, keys[u]);
+        parts[u] = m < m1 && keyfn(m, keys[u]);
       }
 #pragma unroll
       for (int u = 0; u < kSelUnroll; ++u) {
         const bool part = parts[u] && ((keys[u] & pmask) == prefix);
         const uint32_t digit = part ? ((keys[u] >> shift) & 255u) : 256u;
         const uint32_t peers = __match_any_sync(0xffffffffu, digit);
-        if (part && lane == __ffs(peers) - 1) atomicAdd(&s_hist[digit], (uint32_t)__popc(peers));
+        if (part && lane == __ffs(peers) - 1) atomicAdd(&sh->hist[digit], (uint32_t)__popc(peers));
       }
     }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      uint32_t loc[8], sum = 0u;
+    cluster.sync();                               // all local histograms complete
+    if (rank == 0) {
+      if (threadIdx.x < 256) {
+        uint32_t tot = 0u;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { loc[i] = s_hist[lane * 8 + i]; sum += loc[i]; }
-      uint32_t incl = sum;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += o;
+        for (int rk = 0; rk < kTopkCluster; ++rk) tot += cluster.map_shared_rank(sh, rk)->hist[threadIdx.x];
+        sh->total[threadIdx.x] = tot;
       }
-      const uint32_t excl = incl - sum;
-      const uint32_t hit = __ballot_sync(0xffffffffu, incl >= (uint32_t)remaining);
-      if (lane == __ffs(hit) - 1) {
-        uint32_t cum = excl;
-        int d = 0;
-        for (; d < 8; ++d) {
-          if (cum + loc[d] >= (uint32_t)remaining) break;
-          cum += loc[d];
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        uint32_t loc[8], sum = 0u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { loc[i] = sh->total[lane * 8 + i]; sum += loc[i]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += o;
         }
-        s_bc[0] = (uint32_t)(lane * 8 + d);
-        s_bc[1] = cum;        // keys below the chosen digit within the current prefix
-        s_bc[2] = loc[d];
+        const uint32_t excl = incl - sum;
+        const uint32_t hit = __ballot_sync(0xffffffffu, incl >= (uint32_t)remaining);
+        if (lane == __ffs(hit) - 1) {
+          uint32_t cum = excl;
+          int d = 0;
+          for (; d < 8; ++d) {
+            if (cum + loc[d] >= (uint32_t)remaining) break;
+            cum += loc[d];
+          }
+          sh->bc[0] = (uint32_t)(lane * 8 + d);
+          sh->bc[1] = cum;        // keys below the chosen digit within the current prefix
+          sh->bc[2] = loc[d];
+        }
       }
     }
-    __syncthreads();
-    const uint32_t digit = s_bc[0];
-    lt_total += (int)s_bc[1];
-    remaining -= (int)s_bc[1];
-    eq = (int)s_bc[2];
+    cluster.sync();                               // decision published; rank 0 is done with remote reads
+    const uint32_t digit = sh0->bc[0];
+    lt_total += (int)sh0->bc[1];
+    remaining -= (int)sh0->bc[1];
+    eq = (int)sh0->bc[2];
     prefix |= digit << shift;
     pmask |= 255u << shift;
-    __syncthreads();
+    cluster.sync();                               // everyone has read bc before rank 0 rewrites it
   }
   T = prefix; n_lt = lt_total; n_eq = eq;
 }
 
+// s_sel / s_count may be distributed-shared-memory pointers into the cluster's rank-0 CTA
 __device__ __forceinline__ void append_selected(bool sel, unsigned long long rec,
                                                 unsigned long long* s_sel, int* s_count) {
   const uint32_t bal = __ballot_sync(0xffffffffu, sel);
@@ -121,17 +146,18 @@ __device__ __forceinline__ float sigmoid_rn(float x) {
 }
 
 // One CTA per (level, image): top-k of the level's objectness, sorted, decoded, filtered.
-__global__ void __launch_bounds__(kTopkThreads)
+__global__ void __cluster_dims__(kTopkCluster, 1, 1) __launch_bounds__(kTopkThreads)
 rpn_topk_decode_kernel(const RpnDev g, const float* __restrict__ proposals_flat,
                        const float* __restrict__ objectness_flat,
                        const float* __restrict__ image_sizes, float4* __restrict__ sbox,
                        float* __restrict__ cscore, uint8_t* __restrict__ alive,
                        uint32_t* __restrict__ runkey) {
-  extern __shared__ unsigned long long s_sel[];  // next_pow2(k) records: ~ordered(logit):32 | r:32
-  __shared__ uint32_t s_hist[256];
-  __shared__ uint32_t s_bc[4];
+  extern __shared__ unsigned long long s_sel[];  // next_pow2(k) records: ~ordered(logit):32 | r:32 (rank 0's is used)
+  __shared__ SelShared s_sh;
   __shared__ int s_count;
-  const int l = blockIdx.x, b = blockIdx.y;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  const int l = blockIdx.x / kTopkCluster, b = blockIdx.y;
   const int n = g.n_l[l], k = g.k_l[l], A = g.A;
   const int HW = g.H[l] * g.W[l];
   const float* __restrict__ obj =
@@ -149,18 +175,23 @@ rpn_topk_decode_kernel(const RpnDev g, const float* __restrict__ proposals_flat,
   int kp = 1;
   while (kp < k) kp <<= 1;
   if (threadIdx.x == 0) s_count = 0;
-  __syncthreads();
+  // this CTA's slice of the level
+  const int slice = (n + kTopkCluster - 1) / kTopkCluster;
+  const int m0 = min((int)rank * slice, n), m1 = min(m0 + slice, n);
+  unsigned long long* sel0 = cluster.map_shared_rank(s_sel, 0);
+  int* count0 = cluster.map_shared_rank(&s_count, 0);
+  cluster.sync();
 
   if (n <= k) {
-    for (int base = 0; base < n; base += blockDim.x) {
+    for (int base = m0; base < m1; base += blockDim.x) {
       const int m = base + threadIdx.x;
       uint32_t key = 0u;
-      const bool sel = m < n && key_logit(m, key);
-      append_selected(sel, ((unsigned long long)key << 32) | ref_index(m < n ? m : 0), s_sel, &s_count);
+      const bool sel = m < m1 && key_logit(m, key);
+      append_selected(sel, ((unsigned long long)key << 32) | ref_index(m < m1 ? m : 0), sel0, count0);
     }
   } else {
     uint32_t T; int n_lt, n_eq;
-    radix_select(key_logit, n, k, s_hist, s_bc, T, n_lt, n_eq);
+    radix_select(key_logit, m0, m1, k, &s_sh, cluster, T, n_lt, n_eq);
     const int need = k - n_lt;  // how many of the n_eq logits equal to the threshold are taken
     uint32_t T2 = 0xffffffffu;
     if (need < n_eq) {
@@ -171,30 +202,31 @@ rpn_topk_decode_kernel(const RpnDev g, const float* __restrict__ proposals_flat,
         return k1 == T;
       };
       int a_, b_;
-      radix_select(key_tie, n, need, s_hist, s_bc, T2, a_, b_);
+      radix_select(key_tie, m0, m1, need, &s_sh, cluster, T2, a_, b_);
     }
-    for (int base = 0; base < n; base += kSelUnroll * blockDim.x) {
+    for (int base = m0; base < m1; base += kSelUnroll * blockDim.x) {
       uint32_t keys[kSelUnroll];
 #pragma unroll
       for (int u = 0; u < kSelUnroll; ++u) {
         const int m = base + u * blockDim.x + threadIdx.x;
         keys[u] = 0xffffffffu;
-        if (m < n) key_logit(m, keys[u]);
+        if (m < m1) key_logit(m, keys[u]);
       }
 #pragma unroll
       for (int u = 0; u < kSelUnroll; ++u) {
         const int m = base + u * blockDim.x + threadIdx.x;
         uint32_t r = 0u;
         bool sel = false;
-        if (m < n) {
+        if (m < m1) {
           r = ref_index(m);
           sel = keys[u] < T || (keys[u] == T && r <= T2);
         }
-        append_selected(sel, ((unsigned long long)keys[u] << 32) | r, s_sel, &s_count);
+        append_selected(sel, ((unsigned long long)keys[u] << 32) | r, sel0, count0);   // into rank 0 via DSMEM
       }
     }
   }
-  __syncthreads();
+  cluster.sync();          // every CTA's survivors are in rank 0's list
+  if (rank != 0) return;   // rank 0 sorts, decodes and filters the k survivors
   for (int i = k + threadIdx.x; i < kp; i += blockDim.x) s_sel[i] = ~0ull;
   __syncthreads();
   // bitonic sort of the kp records, ascending: logit descending, ties by reference index
@@ -297,7 +329,7 @@ rpn_merge_kernel(const RpnDev g, int post_nms_top_n, const float4* __restrict__ 
 
 struct RpnBuffers {
   float4* sbox; float* cscore; uint8_t* alive; uint32_t* runkey; int32_t* compact;
-  int32_t* run_count; unsigned long long* keepbits; unsigned long long* mask;
+  int32_t* run_count; unsigned long long* keepbits; unsigned long long* diag_cols; unsigned long long* mask;
 };
 
 static int fill_geometry(const dgod_rpn_config* cfg, RpnDev& g, int flat) {
@@ -336,6 +368,7 @@ static size_t carve_rpn(Workspace& ws, RpnBuffers& b, const RpnDev& g) {
   b.compact = ws.take<int32_t>(n_pos);
   b.run_count = ws.take<int32_t>((size_t)(g.n_img > 0 ? g.n_img : 1) * DGOD_MAX_LEVELS);
   b.keepbits = ws.take<unsigned long long>(n_pos / 64 + 1);
+  b.diag_cols = ws.take<unsigned long long>(n_pos);
   b.mask = ws.take<unsigned long long>(n_pos * nms_mask_row_words(max_k));
   return ws.used;
 }
@@ -371,12 +404,12 @@ static int rpn_run(const dgod_rpn_config* cfg, RpnDev& g, const float* proposals
   DGOD_CUDA(cudaMemsetAsync(b.keepbits, 0, ((size_t)n_pos / 64 + 1) * sizeof(unsigned long long), st));
   DGOD_CUDA(cudaMemsetAsync(b.run_count, 0, (size_t)g.n_img * DGOD_MAX_LEVELS * sizeof(int32_t), st));
 
-  rpn_topk_decode_kernel<<<dim3(g.n_levels, g.n_img), kTopkThreads, smem, st>>>(
+  rpn_topk_decode_kernel<<<dim3(g.n_levels * kTopkCluster, g.n_img), kTopkThreads, smem, st>>>(
       g, proposals_flat, objectness_flat, image_sizes, b.sbox, b.cscore, b.alive, b.runkey);
   DGOD_LAUNCHED();
-  int rc = launch_nms_mask(b.sbox, b.runkey, n_pos, max_k, float_round_down(cfg->nms_thresh), b.mask, st);
+  int rc = launch_nms_mask(b.sbox, b.runkey, n_pos, max_k, float_round_down(cfg->nms_thresh), b.mask, b.diag_cols, st);
   if (rc) return rc;
-  rc = launch_nms_scan(b.mask, b.runkey, b.alive, n_pos, max_k, b.keepbits, b.compact, b.run_count, st);
+  rc = launch_nms_scan(b.mask, b.diag_cols, b.runkey, b.alive, n_pos, max_k, b.keepbits, b.compact, b.run_count, st);
   if (rc) return rc;
   rpn_merge_kernel<<<dim3(cdiv(g.k_tot, 256), g.n_img), 256, 0, st>>>(
       g, cfg->post_nms_top_n, b.sbox, b.cscore, b.compact, b.run_count, out_boxes, out_scores, out_count);
