@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""torch.profiler view of one dg mode cycle of bench.py's workload: GPU time by kernel and the
+wall time per training step (to see what the hot-path kernels leave on the table)."""
+import sys, time
+from pathlib import Path
+import torch
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import bench
+from dgod_b200.dg import DGFRCNN
+
+dev = torch.device("cuda")
+torch.backends.cudnn.benchmark = True
+torch.manual_seed(0)
+B = 8
+model = DGFRCNN(9, B, "dg", bench.REG_WEIGHTS, 2).to(dev).train().to(memory_format=torch.channels_last)
+res = [bench.to_device(b, dev) for b in bench.synthetic_batches(4, B, 2, 0)]
+bench.calibrate(model, res[0][0])
+opt = model.configure_optimizer(lr=bench.BENCH_LR)
+
+def step(b):
+    loss = model.training_step(b)
+    opt.zero_grad(set_to_none=True)
+    loss.backward()
+    opt.step()
+
+for _ in range(2):
+    for s in range(8):
+        step(res[(s // 2) % 4])
+torch.cuda.synchronize()
+for s in range(8):
+    mode = model.mode
+    t0 = time.perf_counter(); step(res[(s // 2) % 4]); torch.cuda.synchronize()
+    print(f"mode {mode}: {1e3 * (time.perf_counter() - t0):7.1f} ms")
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for s in range(8):
+        step(res[(s // 2) % 4])
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=40, max_name_column_width=70))
