@@ -78,6 +78,20 @@ __device__ __forceinline__ float iou_exact(const float4 a, float area_a, const f
   return __fdiv_rn(inter, uni);
 }
 
+// Same value, bit for bit, without the IEEE division for disjoint boxes: inter == +0 and a positive
+// union give exactly +0 (the common case of an anchor far from a ground truth).
+__device__ __forceinline__ float iou_exact_skip(const float4 a, float area_a, const float4 b,
+                                                float area_b) {
+  float lx = fmaxf(a.x, b.x), ly = fmaxf(a.y, b.y);
+  float rx = fminf(a.z, b.z), ry = fminf(a.w, b.w);
+  float w = fmaxf(__fsub_rn(rx, lx), 0.f);
+  float h = fmaxf(__fsub_rn(ry, ly), 0.f);
+  float inter = __fmul_rn(w, h);
+  float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  if (inter == 0.f && uni > 0.f) return 0.f;
+  return __fdiv_rn(inter, uni);
+}
+
 // Monotone map float -> uint32 (a < b  <=>  key(a) < key(b) for non-NaN values).
 __device__ __forceinline__ uint32_t float_ordered(float f) {
   uint32_t u = __float_as_uint(f);

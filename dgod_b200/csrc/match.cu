@@ -73,9 +73,9 @@ iou_rowmax_kernel(const float* __restrict__ gt_boxes, const int32_t* __restrict_
     __syncthreads();
     for (int m = 0; m < cnt; ++m) {
       uint32_t key = 0u;
-      if (active) key = float_ordered(iou_exact(tile.box[m], tile.area[m], bx, ba));
+      if (active) key = float_ordered(iou_exact_skip(tile.box[m], tile.area[m], bx, ba));
       key = __reduce_max_sync(0xffffffffu, key);
-      if ((threadIdx.x & 31) == 0) atomicMax(&smax[m], key);
+      if ((threadIdx.x & 31) == 0 && key > smax[m]) atomicMax(&smax[m], key);   // smax only grows: a stale read is safe
     }
     __syncthreads();
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) atomicMax(&gt_max[c0 + i], smax[i]);
@@ -119,7 +119,7 @@ iou_match_kernel(const float* __restrict__ gt_boxes, const int64_t* __restrict__
     __syncthreads();
     if (active) {
       for (int m = 0; m < cnt; ++m) {
-        float v = iou_exact(tile.box[m], tile.area[m], bx, ba);
+        float v = iou_exact_skip(tile.box[m], tile.area[m], bx, ba);
         // Tensor.max(dim=0) keeps the first maximal index; NaN wins like in torch.
         if (best_m < 0 || v > best || (v != v && best == best)) { best = v; best_m = c0 - g0 + m; }
         if (gt_max) tie_with_rowmax |= (float_ordered(v) == smax[m]);

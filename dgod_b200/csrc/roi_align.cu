@@ -12,6 +12,7 @@
 // stores coalesce, and the 4-tap gathers of neighbouring bins hit the same L1 lines.
 // Backward (algo 1): the same sweep scattering with fp32 atomics into zero-filled gradients.
 #include "roi_common.cuh"
+#include <stdlib.h>
 
 namespace dgod {
 
@@ -166,6 +167,22 @@ int msroi_bwd_fast(const dgod_roi_config* cfg, const RoiDev& g, const void* grad
 size_t msroi_bwd_workspace(int n_rois);
 int msroi_bwd_red(const dgod_roi_config* cfg, const RoiDev& g, const void* grad_out, const float* rois,
                   int n_rois, cudaStream_t st, int* handled);
+// TMA paths (roi_align_tma.cu): channels_last, 7x7 bins, sampling ratio 1..2
+int msroi_fwd_tma(const dgod_roi_config* cfg, const RoiDev& g, const float* rois, int n_rois, void* out,
+                  cudaStream_t st, int* handled);
+int msroi_bwd_tma(const dgod_roi_config* cfg, const RoiDev& g, const void* grad_out, const float* rois, int n_rois,
+                  const int32_t* roi_img_offsets, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                  int* handled);
+
+// DGOD_FWD_ALGO=1 keeps the forward on the table-driven kernel (A/B measurements); default: TMA path first.
+static int fwd_algo_from_env() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DGOD_FWD_ALGO");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
 
 }  // namespace dgod
 
@@ -186,6 +203,10 @@ extern "C" int dgod_msroi_align_fwd(const dgod_roi_config* cfg, const void* cons
   }
   cudaStream_t st = (cudaStream_t)stream;
   int handled = 0;
+  if (fwd_algo_from_env() == 0) {
+    rc = msroi_fwd_tma(cfg, g, rois, n_rois, out, st, &handled);
+    if (rc || handled) return rc;
+  }
   rc = msroi_fwd_fast(cfg, g, rois, n_rois, out, st, &handled);
   if (rc || handled) return rc;
   if (cfg->dtype == DGOD_F32) {
@@ -210,7 +231,7 @@ extern "C" int dgod_msroi_align_bwd(const dgod_roi_config* cfg, const void* grad
   int rc = fill_roi_dev(cfg, g);
   if (rc) return rc;
   DGOD_REQUIRE(n_rois >= 0, "roi_align: negative n_rois");
-  DGOD_REQUIRE(algo >= 0 && algo <= 2, "roi_align: unknown backward algorithm");
+  DGOD_REQUIRE(algo >= 0 && algo <= 3, "roi_align: unknown backward algorithm");
   DGOD_REQUIRE(grad_feats, "roi_align: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t esz = cfg->dtype == DGOD_F32 ? 4 : 2;
@@ -220,9 +241,15 @@ extern "C" int dgod_msroi_align_bwd(const dgod_roi_config* cfg, const void* grad
   }
   if (g.B == 0) return DGOD_OK;
   DGOD_REQUIRE(n_rois == 0 || (grad_out && rois), "roi_align: null pointer");
-  // algo 0 (auto): fp32 gradients take the scatter path (16-byte vector reductions on channels_last,
-  // scalar atomics on NCHW) — measured faster than the tile gather on B200; bf16 gradients and
-  // algo 2 take the deterministic tile gather, which accumulates in fp32 and rounds once.
+  // algo 0 (auto): the TMA bulk-reduce path when the shape allows (channels_last, 7x7, sr 1..2), else
+  // fp32 gradients take the scatter path (16-byte vector reductions on channels_last, scalar atomics
+  // on NCHW) and bf16 gradients the deterministic tile gather (fp32 accumulation, one rounding).
+  if (algo == 0 || algo == 3) {
+    int handled = 0;
+    rc = msroi_bwd_tma(cfg, g, grad_out, rois, n_rois, roi_img_offsets, workspace, workspace_bytes, st, &handled);
+    if (rc || handled) return rc;
+    DGOD_REQUIRE(algo == 0, "roi_align: the TMA backward does not support this configuration");
+  }
   const bool want_tile = algo == 2 || (algo == 0 && cfg->dtype != DGOD_F32);
   if (want_tile && n_rois > 0) {
     int handled = 0;

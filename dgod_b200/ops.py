@@ -137,10 +137,12 @@ def _nms_batched_op(boxes: Tensor, scores: Tensor, groups: Optional[Tensor], val
     info = torch.zeros(n_seg + 1, dtype=torch.int32, device=dev)  # counts..., status
     ws_bytes = lib.dgod_nms_workspace_bytes(n_total, n_seg, max_seg_len)
     ws = _ws(ws_bytes, dev)
+    tok = KernelTimer.start("nms_batched", 28 * n_total + 8 * keep.numel())
     check(lib.dgod_nms_batched(_p(boxes), _p(scores), _p(groups), _p(valid), _p(seg_offsets), n_seg,
                                n_total, max_seg_len, float(iou_threshold), int(offset_mode),
                                int(max_out_per_seg), _p(keep), _p(info),
                                C.c_void_p(info.data_ptr() + 4 * n_seg), _p(ws), ws_bytes, _stream()))
+    KernelTimer.stop(tok)
     return keep, info
 
 
@@ -246,11 +248,15 @@ def _iou_match_op(gt_boxes: Tensor, gt_labels: Optional[Tensor], gt_offsets: Ten
     mb = torch.empty(shape + (4,) if want & 8 else (0,), dtype=torch.float32, device=dev)
     wsb = lib.dgod_iou_match_workspace_bytes(n_img, total_gt)
     ws = _ws(wsb, dev)
+    n_out = idx.numel()
+    tok = KernelTimer.start("iou_match", 16 * total_gt + 16 * n_boxes + n_out * (8 + (4 if want & 1 else 0) + (8 if want & 2 else 0)
+                                                                                + (8 if want & 4 else 0) + (16 if want & 8 else 0)))
     check(lib.dgod_iou_match(_p(gt_boxes), _p(gt_labels), _p(gt_offsets), n_img, total_gt, _p(boxes),
                              _p(box_offsets), n_boxes, int(max_boxes_per_img), float(high), float(low),
                              int(allow_low_quality), _p(idx), _p(lf) if want & 1 else None,
                              _p(li) if want & 2 else None, _p(ci) if want & 4 else None,
                              _p(mb) if want & 8 else None, _p(ws), wsb, _stream()))
+    KernelTimer.stop(tok)
     return [idx, lf, li, ci, mb]
 
 
@@ -317,10 +323,13 @@ def _fcos_assign_op(anchors: Tensor, n_first: int, n_last: int, radius: float, g
         cls = torch.empty((0,), dtype=torch.int64, device=dev)
         bt = torch.empty((0,), dtype=torch.float32, device=dev)
         oh = torch.empty((0,), dtype=torch.float32, device=dev)
+    tok = KernelTimer.start("fcos_assign", 16 * n + 16 * gt_boxes.shape[0]
+                            + n_img * n * (8 + ((8 + 16 + 4 * num_classes) if want_targets else 0)))
     check(lib.dgod_fcos_assign(_p(anchors), n, int(n_first), int(n_last), float(radius), _p(gt_boxes),
                                _p(gt_labels), _p(gt_offsets), n_img, _p(idx),
                                _p(cls) if want_targets else None, _p(bt) if want_targets else None,
                                _p(oh) if want_targets else None, int(num_classes), _stream()))
+    KernelTimer.stop(tok)
     return [idx, cls, bt, oh]
 
 
@@ -621,8 +630,12 @@ def rpn_proposals(objectness: Sequence[Tensor], pred_bbox_deltas: Sequence[Tenso
     ws = _ws(wsb, dev)
     op, _k1 = _level_ptrs(obj)
     dp, _k2 = _level_ptrs(dl)
+    n_anchor = sum(o.shape[1] * o.shape[2] * o.shape[3] for o in obj)
+    k_tot = sum(min(pre_nms_top_n, o.shape[1] * o.shape[2] * o.shape[3]) for o in obj)
+    tok = KernelTimer.start("rpn_proposals", n_img * (4 * n_anchor + 16 * k_tot + 20 * post_nms_top_n))
     check(lib.dgod_rpn_proposals(C.byref(cfg), op, dp, _p(image_sizes), _p(boxes), _p(scores), _p(counts),
                                  _p(ws), wsb, _stream()))
+    KernelTimer.stop(tok)
     return boxes, scores, counts
 
 
@@ -684,8 +697,10 @@ def detect_candidates(class_logits: Tensor, box_regression: Tensor, proposals: T
     cs = torch.empty((n_rows, n_cls - 1), dtype=torch.float32, device=dev)
     cl = torch.empty((n_rows, n_cls - 1), dtype=torch.int64, device=dev)
     cv = torch.empty((n_rows, n_cls - 1), dtype=torch.uint8, device=dev)
+    tok = KernelTimer.start("detect_candidates", n_rows * (4 * n_cls + 16 * n_cls + 16) + n_rows * (n_cls - 1) * 29)
     check(_lib.load().dgod_detect_candidates(_p(lg), _p(rg), _p(pr), _p(off), _p(_f32c(image_sizes)),
                                              len(boxes_per_image), n_rows, n_cls, *[float(w) for w in weights],
                                              float(bbox_xform_clip), float(score_thresh), float(min_size),
                                              _p(cb), _p(cs), _p(cl), _p(cv), _stream()))
+    KernelTimer.stop(tok)
     return cb, cs, cl, cv

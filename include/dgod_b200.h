@@ -194,14 +194,16 @@ int dgod_msroi_align_fwd(const dgod_roi_config* cfg /*host*/,
                          const float* rois, int n_rois, void* out, dgod_stream_t stream);
 size_t dgod_msroi_align_bwd_workspace_bytes(int n_rois);
 /* grad_feats[l] is fully overwritten (zero where no RoI contributes): no memset required.
- * algo 0 picks the deterministic tile-gather kernel when the shape allows (sampling_ratio 1..2,
- * C % 64 == 0), else the atomic scatter; workspace is only used by the tile-gather path. */
+ * algo 0 picks the TMA bulk-reduce kernel when the shape allows (channels_last, 7x7 bins,
+ * sampling_ratio 1..2, 64 <= C <= 256, C % 32 == 0), else the vector-RED / atomic scatter (fp32) or
+ * the deterministic tile gather (bf16); 1 forces the scatter, 2 the tile gather, 3 the TMA kernel.
+ * workspace: dgod_msroi_align_bwd_workspace_bytes(n_rois) bytes (RoI records / work counters). */
 int dgod_msroi_align_bwd(const dgod_roi_config* cfg /*host*/,
                          const void* grad_out /*device [K,C,PH,PW]*/,
                          const float* rois, int n_rois,
                          const int32_t* roi_img_offsets /*device [batch+1] or NULL*/,
                          void* const* grad_feats /*host array of device ptrs*/,
-                         int algo /*0 auto, 1 atomic scatter, 2 tile gather*/,
+                         int algo /*0 auto, 1 scatter, 2 tile gather, 3 TMA bulk reduce*/,
                          void* workspace, size_t workspace_bytes, dgod_stream_t stream);
 
 /* ------------------------------------------------------------------ box head post-processing */

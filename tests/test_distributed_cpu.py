@@ -1,0 +1,70 @@
+"""World-size-2 gloo test of the data-parallel plumbing: the path shards by image,
+the only collective is the flat gradient all-reduce (mean) of dg.allreduce_gradients, issued with
+parameter subsets that differ by training mode but are identical across ranks."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dgod_b200.dg import allreduce_gradients
+        torch.manual_seed(0)                                   # identical replicas
+        net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3), torch.nn.Linear(3, 2))
+        params = list(net.parameters())
+        g = torch.Generator().manual_seed(100 + rank)          # each rank owns different images
+        x = torch.randn(4, 6, generator=g)
+        # "mode" step: the last layer is unused -> its parameters have no gradient on any rank
+        loss = net[2](net[1](net[0](x))).square().mean()
+        loss.backward()
+        assert params[-1].grad is None
+        local = [p.grad.clone() if p.grad is not None else None for p in params]
+        allreduce_gradients(params, world)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, local)
+        for i, p in enumerate(params):
+            if p.grad is None:
+                assert all(gl[i] is None for gl in gathered)
+                continue
+            mean = sum(gl[i] for gl in gathered) / world
+            torch.testing.assert_close(p.grad, mean, rtol=1e-6, atol=1e-7)
+        # whole-job throughput accounting of bench.py: max over ranks of the per-rank time
+        t = torch.tensor([10.0 + rank])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert t.item() == 10.0 + world - 1
+        if rank == 0:
+            out.put("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world_size_2():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get() == "ok"
+
+
+def test_single_rank_is_a_no_op():
+    from dgod_b200.dg import allreduce_gradients
+    p = torch.nn.Parameter(torch.ones(3))
+    p.grad = torch.full((3,), 2.0)
+    allreduce_gradients([p], 1)
+    assert torch.equal(p.grad, torch.full((3,), 2.0))

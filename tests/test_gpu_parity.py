@@ -258,7 +258,9 @@ def test_multiscale_roi_align(dtype, tol, nhwc):
         go = go.to(dtype).float()
     grads = O.msroi_align_bwd(go.numpy(), [tuple(f.shape) for f in feats], rois.numpy(), scales, 2, 2, 5)
     from dgod_b200 import ops
-    for algo in ((1, 2) if dtype == torch.float32 else (2,)):      # atomic scatter / tile gather
+    # atomic scatter / tile gather / TMA bulk reduce (channels_last only) / auto
+    algos = ((1, 2) if dtype == torch.float32 else (2,)) + ((3,) if nhwc else ()) + (0,)
+    for algo in algos:
         ops.BACKWARD_ALGO = algo
         try:
             for t in x.values():
@@ -271,6 +273,49 @@ def test_multiscale_roi_align(dtype, tol, nhwc):
             assert gg.dtype == dtype and gg.shape == gr.shape
             assert gg.is_contiguous(memory_format=torch.channels_last if nhwc else torch.contiguous_format)
             np.testing.assert_allclose(gg.float().cpu().numpy(), gr, rtol=tol, atol=tol * max(np.abs(gr).max(), 1e-3))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("with_offsets", [True, False])
+def test_multiscale_roi_align_tma_paths(dtype, tol, with_offsets):
+    """The TMA kernels (channels_last, C = 256, 7x7, sr 2) on the shapes that stress them: footprints
+    wider / taller than one 32-pixel chunk (whole-image RoIs on every level), sub-pixel RoIs, RoIs
+    hanging over every border, an RoI completely outside, and the per-image persistent schedule
+    (roi_img_offsets) vs the plain one."""
+    from dgod_b200 import ops
+    img_h, img_w, C, B = 352, 1344, 256, 3
+    feats = synth.random_features(B, C, img_h, img_w, seed=11)
+    if dtype == torch.bfloat16:
+        feats = [f.to(dtype).float() for f in feats]
+    special = torch.tensor([[0.0, 0.0, img_w, img_h], [-50.0, -60.0, img_w + 70, img_h + 80], [7.0, 9.0, 7.4, 9.3],
+                            [img_w - 3.0, 2.0, img_w + 40, 30.0], [img_w + 10.0, img_h + 10.0, img_w + 60, img_h + 90],
+                            [5.0, 5.0, 1300.0, 40.0], [20.0, 3.0, 60.0, 349.0], [100.0, 100.0, 100.0, 100.0]])
+    boxes = [torch.cat([_boxes(200, 20 + i, img_h, img_w), special]) for i in range(B)]
+    rois = synth.rois_from_boxes(boxes)
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+    ref = O.msroi_align_fwd([f.numpy() for f in feats], rois.numpy(), scales, 7, 7, 2, 2, 5)
+    xs = [f.to(DEV).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True) for f in feats]
+    offs = ops._offsets([b.shape[0] for b in boxes], DEV) if with_offsets else None
+    got = ops.multiscale_roi_align(xs, rois.to(DEV), scales, 7, 2, 2, 5, roi_img_offsets=offs)
+    np.testing.assert_allclose(got.detach().float().cpu().numpy(), ref, rtol=tol, atol=tol * np.abs(ref).max())
+    go = torch.randn(ref.shape, generator=synth.gen(12))
+    if dtype == torch.bfloat16:
+        go = go.to(dtype).float()
+    grads = O.msroi_align_bwd(go.numpy(), [tuple(f.shape) for f in feats], rois.numpy(), scales, 2, 2, 5)
+    ops.BACKWARD_ALGO = 3
+    try:
+        for rep in range(2):        # twice: the outputs must be overwritten, not accumulated
+            for t in xs:
+                t.grad = None
+            got.backward(go.to(DEV).to(dtype), retain_graph=True)
+    finally:
+        ops.BACKWARD_ALGO = 0
+    for x, gr in zip(xs, grads):
+        np.testing.assert_allclose(x.grad.float().cpu().numpy(), gr, rtol=tol, atol=tol * max(np.abs(gr).max(), 1e-3))
+    # size-independent property: every in-range sample spreads weight 1/count, so the gradient of
+    # sum(out) sums to (#valid samples / count) per channel == sum of the oracle's gradient
+    tot = sum(float(x.grad.float().sum()) for x in xs)
+    np.testing.assert_allclose(tot, sum(float(g.astype(np.float64).sum()) for g in grads), rtol=5e-3 if dtype == torch.bfloat16 else 1e-4)
 
 
 def test_roi_align_empty_and_errors():
