@@ -6,46 +6,50 @@
 // contiguous span of (x1-x0+1)*C*s bytes.  Both kernels move whole footprint rows with the bulk
 // async-copy engine instead of issuing per-tap loads / per-tap reductions from the SM lanes:
 //
-//   forward   cp.async.bulk global->shared (mbarrier complete_tx) streams the footprint rows
-//             through a 2-stage ring; the pooled [C][PH*PW] block leaves as one bulk store.
+//   forward   cp.async.bulk global->shared (mbarrier complete_tx) streams the live footprint rows
+//             through a multi-stage ring (up to 8 rows in flight per CTA); the pooled [C][49]
+//             block leaves as one bulk store.
 //   backward  each footprint row is assembled in shared memory and added to the gradient map by
-//             ONE cp.reduce.async.bulk (UBLKRED) — the L2 does the read-modify-write, the SM
-//             issues one instruction per row instead of 16 RED per output element (the previous
-//             kernel was bound by the SM's RED issue rate, ~1.3 cycles per lane).
+//             ONE cp.reduce.async.bulk (SASS UBLKRED) — the L2 does the read-modify-write.  The
+//             previous kernel issued 16 RED per output element and was bound by the SM's RED
+//             issue rate (~1.3 cycles per lane).
 //
 // Arithmetic: bilinear pooling is separable.  With A_y[y][ph] = sum over the sampling rows of bin
-// ph of the weight they put on feature row y (and A_x likewise),
-//       out[c][ph][pw]  = sum_y A_y[y][ph] * ( sum_x A_x[x][pw] * f[y][x][c] ) / count
+// ph of the weight they put on feature row y (and the per-sample column taps likewise),
+//       out[c][ph][pw]  = sum_y A_y[y][ph] * ( sum_{sx in pw} h*f[y][xlo][c] + l*f[y][xhi][c] ) / count
 //       grad_f[y][x][c] = sum_pw A_x[x][pw] * ( sum_ph A_y[y][ph] * g[c][ph][pw] ) / count
-// One thread owns one channel and keeps the PH*PW (= 49) pooled values / gradients of that channel
-// in registers; the A tables are built once per RoI in shared memory and read as warp broadcasts.
-// Out-of-range samples (TV's skip rule) and the border clamp are encoded in the tables by the same
-// axis_tap() the exact kernels use.  The summation order differs from the CPU kernel's
-// sample-by-sample order, i.e. results agree to fp32 rounding (tests: 1e-5 relative), not bitwise.
+// One thread owns one channel and keeps the 49 pooled values / gradients of that channel in
+// registers; the tables are built once per RoI in shared memory and read as warp broadcasts.  A
+// sampling axis has at most 2*PH*sr = 28 live rows (columns) however large the RoI is, so rows
+// are visited through a compact list; RoIs whose column span exceeds 32 pixels switch from one
+// span per row to one 2-pixel slot per sample ("slot mode").  Out-of-range samples (TV's skip
+// rule) and the border clamp come from the same axis_tap() the exact kernels use.  The summation
+// order differs from the CPU kernel's sample-by-sample order: results agree to fp32 rounding
+// (tests: 1e-5 relative), not bitwise.
 //
 // Roofline: HBM.  Forward reads every touched feature line once (the image's maps stay in the
-// 126 MB L2 while its RoIs are in flight) and writes K*C*49*s; backward reads K*C*49*s and writes
-// every gradient line once: a cooperative persistent grid zero-fills image b, grid-syncs, then
-// reduces image b's RoIs, so the read-modify-write traffic stays in L2 and DRAM sees one write.
+// 126 MB L2 while its RoIs are in flight) and writes K*C*49*s.  Backward reads K*C*49*s and
+// writes every gradient line once: a persistent cooperative grid zero-fills image b+1 while it
+// reduces image b's RoIs (per-image completion counters, no grid-wide barrier), so the
+// read-modify-write traffic stays in L2 and DRAM sees each line once.  Measured on B200
+// (tools/microbench/tma_bulk.cu): bulk reduce 5.8 TB/s into an L2-resident region, 3.0 TB/s into
+// a 400 MB one (DRAM read-modify-write); bulk load up to 17 TB/s on L2 hits.
 #include "roi_common.cuh"
-#include <cooperative_groups.h>
-
-namespace cg = cooperative_groups;
 
 namespace dgod {
 
-constexpr int kTmaThreadsMax = 256;   // one thread per channel
-constexpr int kFpCols = 32;           // footprint columns handled per pass (chunked beyond)
-constexpr int kFpRows = 32;           // footprint rows per table build (chunked beyond)
-constexpr int kP = 7;                 // pooled size handled by these kernels (PH = PW = 7)
-constexpr int kPP = 8;                // table pitch (floats)
-constexpr int kMaxSamp = 16;          // samples per axis (PH * sampling_ratio)
+constexpr int kP = 7;                  // pooled size handled by these kernels (PH = PW = 7)
+constexpr int kNB = kP * kP;
+constexpr int kMaxSamp = 14;           // samples per axis (kP * sampling_ratio, sr <= 2)
+constexpr int kMaxLive = 2 * kMaxSamp; // live rows / columns per axis
+constexpr int kSpanMax = 32;           // widest column span moved as one piece per row
+constexpr int kStagesMax = 8;
+constexpr int kFwdRing = 96 * 1024;    // forward: row ring (also the output staging block)
+constexpr int kBwdRing = 64 * 1024;    // backward: gradient-block staging, then the row buffers
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -86,332 +90,449 @@ template <> __device__ __forceinline__ void bulk_reduce_add<__nv_bfloat16>(void*
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
 
-// ---------------------------------------------------------------- per-RoI tables
-struct AxisSamples {       // the PH*sr sampling coordinates of one axis, reduced to taps
-  short lo[kMaxSamp], hi[kMaxSamp];
-  float l[kMaxSamp], h[kMaxSamp];   // both zero when the sample is skipped (out of range)
-  int first, last;                  // footprint extent over the valid samples (first > last: empty)
-};
+// ---------------------------------------------------------------- per-RoI tables (shared memory)
+struct TapEntry { unsigned off_lo, off_hi; float h, l; };   // byte offsets inside a row buffer + weights
 
-struct RoiTables {
+struct alignas(16) RoiSmem {
+  alignas(16) float ay[kMaxLive][8];   // dense A_y of the live rows (list order)
+  alignas(16) float ax[kSpanMax][8];   // backward, span mode: dense A_x of the span's columns
+  alignas(16) TapEntry xs[kMaxSamp];   // column taps of every sample (row-buffer byte offsets)
+  alignas(8) unsigned long long full[kStagesMax];
+  alignas(8) unsigned long long gbar;  // backward: gradient block landed
   RoiGeom geo;
-  AxisSamples sy, sx;
-  float ay[kFpRows][kPP];   // A_y for rows  y0c .. y0c + kFpRows - 1 of the current chunk
-  float ax[kFpCols][kPP];   // A_x for columns of the current chunk
-  unsigned row_live;        // bit r: row r of the chunk receives any weight
+  short ylo[kMaxSamp], yhi[kMaxSamp], xlo[kMaxSamp], xhi[kMaxSamp];
+  float yl[kMaxSamp], yh[kMaxSamp], xl[kMaxSamp], xh[kMaxSamp];   // both zero: sample skipped
+  short rows[kMaxLive];                // live feature rows, ascending
+  short slot_of[kMaxSamp];             // slot mode: compact slot index of a valid sample (-1 otherwise)
+  int n_rows, x_first, x_last, n_slots, slot_mode;
+  int next_k;
 };
 
-// Threads 0..n-1 of a warp fill one axis; extent is reduced with shuffles.
-__device__ __forceinline__ void fill_samples(AxisSamples& s, int lane, int n, int sr, float start, float bin, int size) {
-  int lo = 0x7fffffff, hi = -1;
+// Lane `lane` < n fills sample `lane` of one axis.
+__device__ __forceinline__ void fill_axis_samples(short* lo, short* hi, float* l, float* h, int lane, int n, int sr,
+                                                  float start, float bin, int size) {
   if (lane < n) {
     const AxisTap a = axis_tap(sample_coord(start, lane / sr, bin, lane % sr, sr), size);
-    s.lo[lane] = (short)a.lo;
-    s.hi[lane] = (short)a.hi;
-    s.l[lane] = a.valid ? a.l : 0.f;
-    s.h[lane] = a.valid ? a.h : 0.f;
-    if (a.valid) { lo = a.lo; hi = a.hi; }
+    lo[lane] = (short)a.lo;
+    hi[lane] = (short)a.hi;
+    l[lane] = a.valid ? a.l : 0.f;
+    h[lane] = a.valid ? a.h : 0.f;
   }
-#pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) {
-    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
-    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
-  }
-  if (lane == 0) { s.first = lo; s.last = hi; }
 }
 
-// A[r][p] for footprint coordinate base + r: thread (r, p), r < nrc, p < kPP.
-__device__ __forceinline__ float axis_weight(const AxisSamples& s, int coord, int p, int sr) {
+// weight the samples of bin p put on coordinate `coord`
+__device__ __forceinline__ float axis_weight(const short* lo, const short* hi, const float* l, const float* h, int coord, int p,
+                                             int sr) {
   float w = 0.f;
-  if (p < kP) {
-    for (int i = 0; i < sr; ++i) {
-      const int q = p * sr + i;
-      if (s.lo[q] == coord) w += s.h[q];
-      if (s.hi[q] == coord) w += s.l[q];   // lo == hi at the clamped border: both weights land here
-    }
+  for (int i = 0; i < sr; ++i) {
+    const int q = p * sr + i;
+    if (lo[q] == coord) w += h[q];
+    if (hi[q] == coord) w += l[q];   // lo == hi at the clamped border: both weights land on the same pixel
   }
   return w;
+}
+
+// Warp 0: compact, ascending list of the rows that receive weight; warp 1: column extent, slot map.
+// Call with all threads after the sample tables are visible; ends with the lists visible.
+template <int SR>
+__device__ __forceinline__ void build_lists(RoiSmem& t, int tid) {
+  constexpr int NS = kP * SR;
+  const int lane = tid & 31;
+  if (tid < 32) {
+    const int s = lane >> 1, is_hi = lane & 1;
+    bool valid = false;
+    int r = 0;
+    if (s < NS) {
+      const bool live = t.yh[s] != 0.f || t.yl[s] != 0.f;
+      valid = live && (is_hi ? (t.yl[s] != 0.f && t.yhi[s] != t.ylo[s]) : true);
+      r = is_hi ? t.yhi[s] : t.ylo[s];
+    }
+    const unsigned same = __match_any_sync(0xffffffffu, valid ? r : (0x10000 + lane));
+    const bool first = valid && (__ffs(same) - 1 == lane);
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < 2 * NS; ++j) {
+      const int rj = __shfl_sync(0xffffffffu, r, j);
+      const int fj = __shfl_sync(0xffffffffu, (int)first, j);
+      rank += (fj && rj < r) ? 1 : 0;
+    }
+    if (first) t.rows[rank] = (short)r;
+    const unsigned m = __ballot_sync(0xffffffffu, first);
+    if (lane == 0) t.n_rows = __popc(m);
+  } else if (tid < 64) {
+    int lo = 0x7fffffff, hi = -1;
+    bool valid = false;
+    if (lane < NS) {
+      valid = t.xh[lane] != 0.f || t.xl[lane] != 0.f;
+      if (valid) { lo = t.xlo[lane]; hi = (t.xl[lane] != 0.f) ? t.xhi[lane] : t.xlo[lane]; }
+    }
+    const unsigned vm = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    }
+    if (lane < NS) t.slot_of[lane] = valid ? (short)__popc(vm & ((1u << lane) - 1u)) : (short)-1;
+    if (lane == 0) {
+      t.x_first = lo;
+      t.x_last = hi;
+      t.n_slots = __popc(vm);
+      t.slot_mode = (hi - lo + 1) > kSpanMax;
+    }
+  }
+  __syncthreads();
+}
+
+template <typename T> __device__ __forceinline__ float ld_elem(const unsigned char* p);
+template <> __device__ __forceinline__ float ld_elem<float>(const unsigned char* p) { return *reinterpret_cast<const float*>(p); }
+template <> __device__ __forceinline__ float ld_elem<__nv_bfloat16>(const unsigned char* p) {
+  return __uint_as_float((unsigned)(*reinterpret_cast<const unsigned short*>(p)) << 16);
 }
 
 // ================================================================================================
 // Forward
 // ================================================================================================
-template <typename T>
-__global__ void __launch_bounds__(kTmaThreadsMax, 2)
+template <typename T, int C, int SR>
+__global__ void __launch_bounds__(C, (C == 256) ? 2 : 4)
 msroi_fwd_tma_kernel(const RoiDev g, const float* __restrict__ rois, int n_rois, T* __restrict__ out) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ RoiTables tb;
-  __shared__ __align__(8) unsigned long long bar[2];
-  const int C = g.C, tid = threadIdx.x, sr = g.sr;
+  constexpr int NS = kP * SR;
+  constexpr int PIX = C * (int)sizeof(T);            // bytes per pixel
+  extern __shared__ __align__(128) unsigned char ring[];
+  __shared__ RoiSmem t;
+  const int tid = threadIdx.x;
   const int k = blockIdx.x;
-  const size_t stage_bytes = (size_t)kFpCols * C * sizeof(T);
-  T* ring[2] = {reinterpret_cast<T*>(smem_raw), reinterpret_cast<T*>(smem_raw + stage_bytes)};
-  T* s_out = reinterpret_cast<T*>(smem_raw);   // [C][49], aliases the ring after the row loop
 
   if (tid == 0) {
-    tb.geo = roi_geometry(g, rois + (size_t)k * 5);
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+    t.geo = roi_geometry(g, rois + (size_t)k * 5);
+#pragma unroll
+    for (int i = 0; i < kStagesMax; ++i) mbar_init(&t.full[i], 1);
     mbar_fence_init();
   }
   __syncthreads();
-  const RoiGeom r = tb.geo;
+  const RoiGeom r = t.geo;
   const bool usable = r.batch >= 0 && r.batch < g.B;
   if (usable) {
-    if (tid < 32) fill_samples(tb.sy, tid, kP * sr, sr, r.start_h, r.bin_h, r.H);
-    else if (tid < 64) fill_samples(tb.sx, tid - 32, kP * sr, sr, r.start_w, r.bin_w, r.W);
+    if (tid < 32) fill_axis_samples(t.ylo, t.yhi, t.yl, t.yh, tid, NS, SR, r.start_h, r.bin_h, r.H);
+    else if (tid < 64) fill_axis_samples(t.xlo, t.xhi, t.xl, t.xh, tid - 32, NS, SR, r.start_w, r.bin_w, r.W);
   }
   __syncthreads();
 
-  float acc[kP * kP];
+  float acc[kNB];
 #pragma unroll
-  for (int i = 0; i < kP * kP; ++i) acc[i] = 0.f;
+  for (int i = 0; i < kNB; ++i) acc[i] = 0.f;
 
-  if (usable && tb.sy.first <= tb.sy.last && tb.sx.first <= tb.sx.last) {
-    const int y_first = tb.sy.first, y_last = tb.sy.last, x_first = tb.sx.first, x_last = tb.sx.last;
-    const T* __restrict__ img = reinterpret_cast<const T*>(g.feat[r.level]) + (size_t)r.batch * r.H * r.W * C;
-    unsigned phase[2] = {0u, 0u};
-    for (int yc = y_first; yc <= y_last; yc += kFpRows) {
-      const int nrows = min(kFpRows, y_last - yc + 1);
-      for (int xc = x_first; xc <= x_last; xc += kFpCols) {
-        const int ncols = min(kFpCols, x_last - xc + 1);
-        __syncthreads();                      // previous chunk done with the tables and the ring
-        for (int e = tid; e < kFpRows * kPP; e += blockDim.x) {   // 32 rows x 8 table columns
-          const int er = e >> 3, ep = e & 7;
-          tb.ay[er][ep] = er < nrows ? axis_weight(tb.sy, yc + er, ep, sr) : 0.f;
-          tb.ax[er][ep] = er < ncols ? axis_weight(tb.sx, xc + er, ep, sr) : 0.f;
+  if (usable) {
+    build_lists<SR>(t, tid);
+    const int n_rows = t.n_rows;
+    if (n_rows > 0 && t.x_first <= t.x_last) {
+      const int x_first = t.x_first, slot_mode = t.slot_mode;
+      const int row_px = slot_mode ? 2 * t.n_slots : (t.x_last - x_first + 1);
+      const unsigned row_bytes = (unsigned)row_px * PIX;              // multiple of 128
+      const int n_stage = min(kStagesMax, kFwdRing / (int)row_bytes);   // >= 3 (row_bytes <= 32 KB)
+      // tables: A_y of the live rows, column taps as byte offsets into a row buffer
+      for (int e = tid; e < kMaxLive * 8; e += C) {
+        const int i = e >> 3, p = e & 7;
+        t.ay[i][p] = (i < n_rows && p < kP) ? axis_weight(t.ylo, t.yhi, t.yl, t.yh, t.rows[i], p, SR) : 0.f;
+      }
+      if (tid < NS) {
+        TapEntry e;
+        const bool valid = t.xh[tid] != 0.f || t.xl[tid] != 0.f;
+        e.h = t.xh[tid];
+        e.l = t.xl[tid];
+        if (!valid) {
+          e.off_lo = e.off_hi = 0u;      // weights are zero; offset 0 is always a loaded pixel
+        } else if (slot_mode) {
+          e.off_lo = (unsigned)t.slot_of[tid] * 2u * PIX;
+          e.off_hi = e.off_lo + ((t.xhi[tid] != t.xlo[tid]) ? PIX : 0u);
+        } else {
+          e.off_lo = (unsigned)(t.xlo[tid] - x_first) * PIX;
+          e.off_hi = (unsigned)(t.xhi[tid] - x_first) * PIX;
         }
-        __syncthreads();
-        if (tid < 32) {
-          bool live = false;
-          if (tid < nrows) {
-#pragma unroll
-            for (int p = 0; p < kP; ++p) live |= tb.ay[tid][p] != 0.f;
-          }
-          const unsigned m = __ballot_sync(0xffffffffu, live);
-          if (tid == 0) tb.row_live = m;
+        t.xs[tid] = e;
+      }
+      __syncthreads();
+      const T* __restrict__ img = reinterpret_cast<const T*>(g.feat[r.level]) + (size_t)r.batch * r.H * r.W * C;
+      auto issue_row = [&](int i) {      // thread 0 only
+        const int st = i % n_stage;
+        const size_t y = (size_t)t.rows[i];
+        unsigned char* dst = ring + (size_t)st * row_bytes;
+        if (!slot_mode) {
+          mbar_expect_tx(&t.full[st], row_bytes);
+          bulk_load(dst, img + (y * r.W + x_first) * C, row_bytes, &t.full[st]);
+        } else {
+          unsigned total = 0;
+          for (int s = 0; s < NS; ++s)
+            if (t.slot_of[s] >= 0) total += (t.xhi[s] != t.xlo[s]) ? 2u * PIX : (unsigned)PIX;
+          mbar_expect_tx(&t.full[st], total);
+          for (int s = 0; s < NS; ++s)
+            if (t.slot_of[s] >= 0)
+              bulk_load(dst + (size_t)t.slot_of[s] * 2 * PIX, img + (y * r.W + t.xlo[s]) * C,
+                        (t.xhi[s] != t.xlo[s]) ? 2u * PIX : (unsigned)PIX, &t.full[st]);
         }
-        __syncthreads();
-        unsigned live = tb.row_live;
-        const unsigned row_bytes = (unsigned)ncols * C * sizeof(T);
-        // software pipeline over the live rows: row i+1 streams in while row i is consumed
-        int cur = live ? __ffs(live) - 1 : -1;
-        int stage = 0;
-        if (cur >= 0 && tid == 0) {
-          mbar_expect_tx(&bar[0], row_bytes);
-          bulk_load(ring[0], img + ((size_t)(yc + cur) * r.W + xc) * C, row_bytes, &bar[0]);
+      };
+      if (tid == 0)
+        for (int i = 0; i < min(n_stage, n_rows); ++i) issue_row(i);
+      for (int i = 0; i < n_rows; ++i) {
+        const int st = i % n_stage;
+        mbar_wait(&t.full[st], (unsigned)(i / n_stage) & 1u);
+        const unsigned char* __restrict__ row = ring + (size_t)st * row_bytes + tid * (int)sizeof(T);
+        float rx[kP];
+#pragma unroll
+        for (int p = 0; p < kP; ++p) rx[p] = 0.f;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const uint4 e = *reinterpret_cast<const uint4*>(&t.xs[s]);
+          const float v0 = ld_elem<T>(row + e.x), v1 = ld_elem<T>(row + e.y);
+          rx[s / SR] = fmaf(__uint_as_float(e.w), v1, fmaf(__uint_as_float(e.z), v0, rx[s / SR]));
         }
-        while (cur >= 0) {
-          live &= live - 1;
-          const int nxt = live ? __ffs(live) - 1 : -1;
-          if (nxt >= 0 && tid == 0) {
-            mbar_expect_tx(&bar[stage ^ 1], row_bytes);
-            bulk_load(ring[stage ^ 1], img + ((size_t)(yc + nxt) * r.W + xc) * C, row_bytes, &bar[stage ^ 1]);
-          }
-          mbar_wait(&bar[stage], phase[stage]);
-          phase[stage] ^= 1u;
-          const T* __restrict__ row = ring[stage] + tid;
-          float rx[kP];
+        const float4 a0 = *reinterpret_cast<const float4*>(&t.ay[i][0]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&t.ay[i][4]);
 #pragma unroll
-          for (int p = 0; p < kP; ++p) rx[p] = 0.f;
-#pragma unroll 4
-          for (int x = 0; x < ncols; ++x) {
-            const float v = to_f32<T>(row[(size_t)x * C]);
-            const float4 w0 = *reinterpret_cast<const float4*>(&tb.ax[x][0]);
-            const float4 w1 = *reinterpret_cast<const float4*>(&tb.ax[x][4]);
-            rx[0] = fmaf(w0.x, v, rx[0]); rx[1] = fmaf(w0.y, v, rx[1]); rx[2] = fmaf(w0.z, v, rx[2]);
-            rx[3] = fmaf(w0.w, v, rx[3]); rx[4] = fmaf(w1.x, v, rx[4]); rx[5] = fmaf(w1.y, v, rx[5]);
-            rx[6] = fmaf(w1.z, v, rx[6]);
-          }
-          const float4 a0 = *reinterpret_cast<const float4*>(&tb.ay[cur][0]);
-          const float4 a1 = *reinterpret_cast<const float4*>(&tb.ay[cur][4]);
-          const float a[kP] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z};
-#pragma unroll
-          for (int ph = 0; ph < kP; ++ph)
-#pragma unroll
-            for (int pw = 0; pw < kP; ++pw) acc[ph * kP + pw] = fmaf(a[ph], rx[pw], acc[ph * kP + pw]);
-          __syncthreads();                    // everyone is done with ring[stage]: it may be refilled
-          cur = nxt;
-          stage ^= 1;
+        for (int pw = 0; pw < kP; ++pw) {
+          acc[0 * kP + pw] = fmaf(a0.x, rx[pw], acc[0 * kP + pw]);
+          acc[1 * kP + pw] = fmaf(a0.y, rx[pw], acc[1 * kP + pw]);
+          acc[2 * kP + pw] = fmaf(a0.z, rx[pw], acc[2 * kP + pw]);
+          acc[3 * kP + pw] = fmaf(a0.w, rx[pw], acc[3 * kP + pw]);
+          acc[4 * kP + pw] = fmaf(a1.x, rx[pw], acc[4 * kP + pw]);
+          acc[5 * kP + pw] = fmaf(a1.y, rx[pw], acc[5 * kP + pw]);
+          acc[6 * kP + pw] = fmaf(a1.z, rx[pw], acc[6 * kP + pw]);
         }
+        __syncthreads();                    // everyone is done with stage st: it may be refilled
+        if (tid == 0 && i + n_stage < n_rows) issue_row(i + n_stage);
       }
     }
   }
   __syncthreads();
-  // pooled block -> shared [C][49] (lane stride 49 words: conflict-free) -> one bulk store
-  const float inv = 1.f / r.count;           // count = sr*sr, a power of two for sr in {1, 2, 4}
-  T* so = s_out + (size_t)tid * (kP * kP);
+  // pooled block -> shared [C][49] (lane stride 49 elements: conflict-free) -> one bulk store
+  const float inv = 1.f / r.count;          // count = sr*sr: a power of two
+  T* so = reinterpret_cast<T*>(ring) + tid * kNB;
 #pragma unroll
-  for (int i = 0; i < kP * kP; ++i) so[i] = from_f32<T>(acc[i] * inv);
+  for (int i = 0; i < kNB; ++i) so[i] = from_f32<T>(acc[i] * inv);
   fence_proxy_async_smem();
   __syncthreads();
   if (tid == 0) {
-    bulk_store(out + (size_t)k * C * (kP * kP), s_out, (unsigned)(C * kP * kP * sizeof(T)));
+    bulk_store(out + (size_t)k * C * kNB, ring, (unsigned)(C * kNB * sizeof(T)));
     bulk_commit();
-    bulk_wait_read_all();
+    bulk_wait_read<0>();
   }
 }
 
 // ================================================================================================
 // Backward
 // ================================================================================================
-// Work of one RoI by one CTA (blockDim.x == C).  smem_raw: gradient block staging [C][49] which is
-// then reused as the two row buffers.
-template <typename T>
-__device__ __forceinline__ void bwd_one_roi(const RoiDev& g, RoiTables& tb, unsigned char* smem_raw, const T* __restrict__ grad_out,
-                                            const float* __restrict__ rois, int k) {
-  const int C = g.C, tid = threadIdx.x, sr = g.sr;
-  __syncthreads();                            // previous RoI of this CTA is completely done with smem
-  if (tid == 0) tb.geo = roi_geometry(g, rois + (size_t)k * 5);
-  __syncthreads();
-  const RoiGeom r = tb.geo;
-  if (r.batch < 0 || r.batch >= g.B) return;
-  {
-    // gradient block of this RoI, contiguous [C][49]: coalesced 16-byte copies into shared memory
-    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(grad_out + (size_t)k * C * (kP * kP));
-    uint4* dst = reinterpret_cast<uint4*>(smem_raw);
-    const int n16 = C * kP * kP * (int)sizeof(T) / 16;
-    for (int i = tid; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+// One RoI by one CTA (blockDim.x == C).  ring: gradient-block staging [C][49], then row buffers.
+template <typename T, int C, int SR>
+__device__ __forceinline__ void bwd_one_roi(const RoiDev& g, RoiSmem& t, unsigned char* ring, const T* __restrict__ grad_out,
+                                            const float* __restrict__ rois, int k, unsigned gbar_parity) {
+  constexpr int NS = kP * SR;
+  constexpr int PIX = C * (int)sizeof(T);
+  const int tid = threadIdx.x;
+  // caller guarantees: no bulk operation of this CTA still reads `ring`, and a __syncthreads() since
+  if (tid == 0) {
+    mbar_expect_tx(&t.gbar, (unsigned)(C * kNB * sizeof(T)));
+    bulk_load(ring, grad_out + (size_t)k * C * kNB, (unsigned)(C * kNB * sizeof(T)), &t.gbar);
+    t.geo = roi_geometry(g, rois + (size_t)k * 5);
   }
-  if (tid < 32) fill_samples(tb.sy, tid, kP * sr, sr, r.start_h, r.bin_h, r.H);
-  else if (tid < 64) fill_samples(tb.sx, tid - 32, kP * sr, sr, r.start_w, r.bin_w, r.W);
   __syncthreads();
-  if (tb.sy.first > tb.sy.last || tb.sx.first > tb.sx.last) return;
-  float gr[kP * kP];
-  {
-    const float inv = 1.f / (float)(sr * sr);   // the CPU backward divides by the raw grid product
-    const T* sg = reinterpret_cast<const T*>(smem_raw) + (size_t)tid * (kP * kP);
-#pragma unroll
-    for (int i = 0; i < kP * kP; ++i) gr[i] = to_f32<T>(sg[i]) * inv;
+  const RoiGeom r = t.geo;
+  const bool usable = r.batch >= 0 && r.batch < g.B;
+  if (usable) {
+    if (tid < 32) fill_axis_samples(t.ylo, t.yhi, t.yl, t.yh, tid, NS, SR, r.start_h, r.bin_h, r.H);
+    else if (tid < 64) fill_axis_samples(t.xlo, t.xhi, t.xl, t.xh, tid - 32, NS, SR, r.start_w, r.bin_w, r.W);
   }
-  const int y_first = tb.sy.first, y_last = tb.sy.last, x_first = tb.sx.first, x_last = tb.sx.last;
-  const size_t stage_bytes = (size_t)kFpCols * C * sizeof(T);
-  T* ring[2] = {reinterpret_cast<T*>(smem_raw), reinterpret_cast<T*>(smem_raw + stage_bytes)};
-  T* __restrict__ img = reinterpret_cast<T*>(g.gfeat[r.level]) + (size_t)r.batch * r.H * r.W * C;
-  for (int yc = y_first; yc <= y_last; yc += kFpRows) {
-    const int nrows = min(kFpRows, y_last - yc + 1);
-    for (int xc = x_first; xc <= x_last; xc += kFpCols) {
-      const int ncols = min(kFpCols, x_last - xc + 1);
-      if (tid == 0) bulk_wait_read_all();     // row buffers of the previous chunk have been read
-      __syncthreads();                        // ... and everyone is done with the staging / tables
-      for (int e = tid; e < kFpRows * kPP; e += blockDim.x) {
-        const int er = e >> 3, ep = e & 7;
-        tb.ay[er][ep] = er < nrows ? axis_weight(tb.sy, yc + er, ep, sr) : 0.f;
-        tb.ax[er][ep] = er < ncols ? axis_weight(tb.sx, xc + er, ep, sr) : 0.f;
-      }
-      __syncthreads();
-      if (tid < 32) {
-        bool live = false;
-        if (tid < nrows) {
-#pragma unroll
-          for (int p = 0; p < kP; ++p) live |= tb.ay[tid][p] != 0.f;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, live);
-        if (tid == 0) tb.row_live = m;
-      }
-      __syncthreads();
-      unsigned live = tb.row_live;
-      const unsigned row_bytes = (unsigned)ncols * C * sizeof(T);
-      int stage = 0;
-      while (live) {
-        const int cur = __ffs(live) - 1;
-        live &= live - 1;
-        const float4 a0 = *reinterpret_cast<const float4*>(&tb.ay[cur][0]);
-        const float4 a1 = *reinterpret_cast<const float4*>(&tb.ay[cur][4]);
-        const float a[kP] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z};
-        float t[kP];
-#pragma unroll
-        for (int pw = 0; pw < kP; ++pw) {
-          float s = 0.f;
-#pragma unroll
-          for (int ph = 0; ph < kP; ++ph) s = fmaf(a[ph], gr[ph * kP + pw], s);
-          t[pw] = s;
-        }
-        T* __restrict__ row = ring[stage] + tid;
-#pragma unroll 4
-        for (int x = 0; x < ncols; ++x) {
-          const float4 w0 = *reinterpret_cast<const float4*>(&tb.ax[x][0]);
-          const float4 w1 = *reinterpret_cast<const float4*>(&tb.ax[x][4]);
-          float v = w0.x * t[0];
-          v = fmaf(w0.y, t[1], v); v = fmaf(w0.z, t[2], v); v = fmaf(w0.w, t[3], v);
-          v = fmaf(w1.x, t[4], v); v = fmaf(w1.y, t[5], v); v = fmaf(w1.z, t[6], v);
-          row[(size_t)x * C] = from_f32<T>(v);
-        }
-        fence_proxy_async_smem();             // generic-proxy writes -> visible to the bulk engine
-        if (tid == 0) bulk_wait_read_all();   // the other buffer (row issued one step ago) has been read
-        __syncthreads();
-        if (tid == 0) {
-          bulk_reduce_add<T>(img + ((size_t)(yc + cur) * r.W + xc) * C, ring[stage], row_bytes);
-          bulk_commit();
-        }
-        stage ^= 1;
+  __syncthreads();
+  int n_rows = 0;
+  if (usable) {
+    build_lists<SR>(t, tid);
+    n_rows = (t.x_first <= t.x_last) ? t.n_rows : 0;
+  }
+  const int x_first = t.x_first, slot_mode = t.slot_mode;
+  const int row_px = n_rows ? (slot_mode ? 2 * t.n_slots : (t.x_last - x_first + 1)) : 1;
+  const unsigned row_bytes = (unsigned)row_px * PIX;
+  const int n_buf = min(4, kBwdRing / (int)row_bytes);        // 2..4 row buffers
+  if (n_rows) {
+    const float inv = 1.f / (float)(SR * SR);                 // the CPU backward divides by the raw grid product
+    for (int e = tid; e < kMaxLive * 8; e += C) {
+      const int i = e >> 3, p = e & 7;
+      t.ay[i][p] = (i < n_rows && p < kP) ? axis_weight(t.ylo, t.yhi, t.yl, t.yh, t.rows[i], p, SR) * inv : 0.f;
+    }
+    if (!slot_mode) {
+      for (int e = tid; e < kSpanMax * 8; e += C) {
+        const int i = e >> 3, p = e & 7;
+        t.ax[i][p] = (i < row_px && p < kP) ? axis_weight(t.xlo, t.xhi, t.xl, t.xh, x_first + i, p, SR) : 0.f;
       }
     }
   }
-  if (tid == 0) bulk_wait_read_all();
+  // the gradient block has landed: 49 values of this thread's channel -> registers
+  mbar_wait(&t.gbar, gbar_parity);
+  float gr[kNB];
+  {
+    const T* sg = reinterpret_cast<const T*>(ring) + tid * kNB;
+#pragma unroll
+    for (int i = 0; i < kNB; ++i) gr[i] = to_f32<T>(sg[i]);
+  }
+  __syncthreads();                          // staging consumed, tables visible
+  if (!n_rows) return;
+  T* __restrict__ img = reinterpret_cast<T*>(g.gfeat[r.level]) + (size_t)r.batch * r.H * r.W * C;
+  for (int i = 0; i < n_rows; ++i) {
+    const float4 a0 = *reinterpret_cast<const float4*>(&t.ay[i][0]);
+    const float4 a1 = *reinterpret_cast<const float4*>(&t.ay[i][4]);
+    float tq[kP];
+#pragma unroll
+    for (int pw = 0; pw < kP; ++pw) {
+      float s = a0.x * gr[0 * kP + pw];
+      s = fmaf(a0.y, gr[1 * kP + pw], s);
+      s = fmaf(a0.z, gr[2 * kP + pw], s);
+      s = fmaf(a0.w, gr[3 * kP + pw], s);
+      s = fmaf(a1.x, gr[4 * kP + pw], s);
+      s = fmaf(a1.y, gr[5 * kP + pw], s);
+      s = fmaf(a1.z, gr[6 * kP + pw], s);
+      tq[pw] = s;
+    }
+    unsigned char* buf = ring + (size_t)(i % n_buf) * row_bytes;
+    T* __restrict__ row = reinterpret_cast<T*>(buf) + tid;
+    if (!slot_mode) {
+#pragma unroll 4
+      for (int x = 0; x < row_px; ++x) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&t.ax[x][0]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&t.ax[x][4]);
+        float v = w0.x * tq[0];
+        v = fmaf(w0.y, tq[1], v); v = fmaf(w0.z, tq[2], v); v = fmaf(w0.w, tq[3], v);
+        v = fmaf(w1.x, tq[4], v); v = fmaf(w1.y, tq[5], v); v = fmaf(w1.z, tq[6], v);
+        row[x * C] = from_f32<T>(v);
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const int slot = t.slot_of[s];
+        if (slot >= 0) {                    // warp-uniform
+          const bool two = t.xhi[s] != t.xlo[s];
+          row[(slot * 2) * C] = from_f32<T>((two ? t.xh[s] : t.xh[s] + t.xl[s]) * tq[s / SR]);
+          if (two) row[(slot * 2 + 1) * C] = from_f32<T>(t.xl[s] * tq[s / SR]);
+        }
+      }
+    }
+    fence_proxy_async_smem();               // generic-proxy writes -> visible to the bulk engine
+    if (tid == 0) {                         // the buffer the NEXT row will write must have been read
+      if (n_buf == 2) bulk_wait_read<0>();
+      else if (n_buf == 3) bulk_wait_read<1>();
+      else bulk_wait_read<2>();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const size_t y = (size_t)t.rows[i];
+      if (!slot_mode) {
+        bulk_reduce_add<T>(img + (y * r.W + x_first) * C, buf, row_bytes);
+      } else {
+        for (int s = 0; s < NS; ++s)
+          if (t.slot_of[s] >= 0)
+            bulk_reduce_add<T>(img + (y * r.W + t.xlo[s]) * C, buf + (size_t)t.slot_of[s] * 2 * PIX,
+                               (t.xhi[s] != t.xlo[s]) ? 2u * PIX : (unsigned)PIX);
+      }
+      bulk_commit();
+    }
+  }
 }
 
 // One CTA per RoI; gradients must have been zero-filled.
-template <typename T>
-__global__ void __launch_bounds__(kTmaThreadsMax, 3)
+template <typename T, int C, int SR>
+__global__ void __launch_bounds__(C, (C == 256) ? 3 : 4)
 msroi_bwd_tma_kernel(const RoiDev g, const T* __restrict__ grad_out, const float* __restrict__ rois, int n_rois) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ RoiTables tb;
-  bwd_one_roi<T>(g, tb, smem_raw, grad_out, rois, blockIdx.x);
+  extern __shared__ __align__(128) unsigned char ring[];
+  __shared__ RoiSmem t;
+  if (threadIdx.x == 0) {
+    mbar_init(&t.gbar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  bwd_one_roi<T, C, SR>(g, t, ring, grad_out, rois, blockIdx.x, 0u);
+  if (threadIdx.x == 0) bulk_wait_read<0>();
 }
 
-// Persistent cooperative variant: per image b, zero-fill the image's gradient maps, grid-sync,
-// reduce the image's RoIs (dynamic work counter).  The zero-filled lines of one image (52.9 MB
-// fp32 at 608x1024) are still dirty in L2 when the reductions arrive, so DRAM sees each line once.
-template <typename T>
-__global__ void __launch_bounds__(kTmaThreadsMax, 3)
+// Persistent cooperative variant.  Every CTA zero-fills its share of image b+1's gradient maps
+// BEFORE it starts on image b's RoIs and publishes that in zero_done[b+1]; an RoI of image b is
+// only started once zero_done[b] == gridDim.x.  All CTAs are co-resident (cooperative launch), so
+// the wait cannot deadlock, and in steady state nobody waits: the zero-filled lines of an image
+// (52.9 MB fp32 at 608x1024) are still dirty in L2 when the reductions arrive.
+template <typename T, int C, int SR>
+__global__ void __launch_bounds__(C, (C == 256) ? 3 : 4)
 msroi_bwd_tma_persistent_kernel(const RoiDev g, const T* __restrict__ grad_out, const float* __restrict__ rois,
                                 const int32_t* __restrict__ roi_img_offsets, int* __restrict__ counters) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ RoiTables tb;
-  __shared__ int s_k;
-  cg::grid_group grid = cg::this_grid();
-  const int C = g.C;
-  for (int b = 0; b < g.B; ++b) {
+  extern __shared__ __align__(128) unsigned char ring[];
+  __shared__ RoiSmem t;
+  int* work = counters;                 // [B] next RoI of image b
+  int* zero_done = counters + g.B;      // [B] CTAs that finished zero-filling image b
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&t.gbar, 1);
+    mbar_fence_init();
+  }
+  auto zero_image = [&](int b) {
     for (int l = 0; l < g.n_levels; ++l) {
       const size_t n16 = (size_t)g.H[l] * g.W[l] * C * sizeof(T) / 16;
       uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<T*>(g.gfeat[l]) + (size_t)b * g.H[l] * g.W[l] * C);
-      for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
-        p[i] = make_uint4(0u, 0u, 0u, 0u);
+      for (size_t i = (size_t)blockIdx.x * C + tid; i < n16; i += (size_t)gridDim.x * C) p[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     asm volatile("fence.proxy.async.global;\n" ::: "memory");   // generic-proxy zeros before the bulk engine's RMW
     __threadfence();
-    grid.sync();
+    __syncthreads();
+    if (tid == 0) atomicAdd(&zero_done[b], 1);
+  };
+  zero_image(0);
+  unsigned n_done = 0;                  // RoIs processed by this CTA (parity of the staging barrier)
+  for (int b = 0; b < g.B; ++b) {
+    if (b + 1 < g.B) zero_image(b + 1);
+    if (tid == 0) {
+      while (atomicAdd(&zero_done[b], 0) < (int)gridDim.x) __nanosleep(200);
+      __threadfence();
+    }
     const int k0 = roi_img_offsets[b], k1 = roi_img_offsets[b + 1];
     while (true) {
+      if (tid == 0) {
+        bulk_wait_read<0>();            // row buffers of the previous RoI have been read
+        t.next_k = k0 + atomicAdd(&work[b], 1);
+      }
       __syncthreads();
-      if (threadIdx.x == 0) s_k = k0 + atomicAdd(&counters[b], 1);
-      __syncthreads();
-      const int k = s_k;
+      const int k = t.next_k;
       if (k >= k1) break;
-      bwd_one_roi<T>(g, tb, smem_raw, grad_out, rois, k);
+      bwd_one_roi<T, C, SR>(g, t, ring, grad_out, rois, k, n_done & 1u);
+      ++n_done;
     }
+    __syncthreads();
   }
+  if (tid == 0) bulk_wait_read<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
 static bool tma_shape_ok(const dgod_roi_config* cfg, const RoiDev& g) {
-  const int esz = cfg->dtype == DGOD_F32 ? 4 : 2;
   if (!g.channels_last || g.PH != kP || g.PW != kP) return false;
   if (g.sr < 1 || g.sr > 2) return false;
-  if (g.C % 32 != 0 || g.C < 64 || g.C > kTmaThreadsMax || (g.C * esz) % 16 != 0) return false;
+  if (!(g.C == 256 || ((g.C == 128 || g.C == 64) && g.sr == 2))) return false;   // instantiated shapes
   for (int l = 0; l < g.n_levels; ++l)
     if (g.H[l] > 32000 || g.W[l] > 32000) return false;
+  (void)cfg;
   return true;
 }
 
-static size_t tma_smem_bytes(const RoiDev& g, int esz) {
-  const size_t ring = 2 * (size_t)kFpCols * g.C * esz;
-  const size_t block = (size_t)g.C * kP * kP * esz;
-  return ring > block ? ring : block;
+template <typename T, int C, int SR>
+static int launch_fwd_tma(const RoiDev& g, const float* rois, int n_rois, void* out, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    DGOD_CUDA(cudaFuncSetAttribute(msroi_fwd_tma_kernel<T, C, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdRing));
+    attr = true;
+  }
+  msroi_fwd_tma_kernel<T, C, SR><<<n_rois, C, kFwdRing, st>>>(g, rois, n_rois, (T*)out);
+  DGOD_LAUNCHED();
+  return DGOD_OK;
+}
+
+template <typename T>
+static int dispatch_fwd_tma(const RoiDev& g, const float* rois, int n_rois, void* out, cudaStream_t st) {
+  if (g.C == 256) return g.sr == 2 ? launch_fwd_tma<T, 256, 2>(g, rois, n_rois, out, st) : launch_fwd_tma<T, 256, 1>(g, rois, n_rois, out, st);
+  if (g.C == 128) return launch_fwd_tma<T, 128, 2>(g, rois, n_rois, out, st);
+  return launch_fwd_tma<T, 64, 2>(g, rois, n_rois, out, st);
 }
 
 int msroi_fwd_tma(const dgod_roi_config* cfg, const RoiDev& g, const float* rois, int n_rois, void* out,
@@ -420,72 +541,54 @@ int msroi_fwd_tma(const dgod_roi_config* cfg, const RoiDev& g, const float* rois
   if (!tma_shape_ok(cfg, g) || ((uintptr_t)out & 15)) return DGOD_OK;
   for (int l = 0; l < g.n_levels; ++l)
     if ((uintptr_t)g.feat[l] & 15) return DGOD_OK;
-  const int esz = cfg->dtype == DGOD_F32 ? 4 : 2;
-  const size_t smem = tma_smem_bytes(g, esz);
-  static size_t attr[2] = {0, 0};
-  if (cfg->dtype == DGOD_F32) {
-    if (smem > attr[0]) {
-      DGOD_CUDA(cudaFuncSetAttribute(msroi_fwd_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr[0] = smem;
-    }
-    msroi_fwd_tma_kernel<float><<<n_rois, g.C, smem, st>>>(g, rois, n_rois, (float*)out);
-  } else {
-    if (smem > attr[1]) {
-      DGOD_CUDA(cudaFuncSetAttribute(msroi_fwd_tma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr[1] = smem;
-    }
-    msroi_fwd_tma_kernel<__nv_bfloat16><<<n_rois, g.C, smem, st>>>(g, rois, n_rois, (__nv_bfloat16*)out);
-  }
-  DGOD_LAUNCHED();
   *handled = 1;
-  return DGOD_OK;
+  return cfg->dtype == DGOD_F32 ? dispatch_fwd_tma<float>(g, rois, n_rois, out, st)
+                                : dispatch_fwd_tma<__nv_bfloat16>(g, rois, n_rois, out, st);
 }
 
-template <typename T>
+template <typename T, int C, int SR>
 static int launch_bwd_tma(const RoiDev& g, const void* grad_out, const float* rois, int n_rois,
                           const int32_t* roi_img_offsets, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  const size_t smem = tma_smem_bytes(g, (int)sizeof(T));
-  static size_t attr = 0, attr_p = 0;
-  static int coop = -1, n_sm = 0;
-  if (coop < 0) {
+  static bool attr = false;
+  static int coop = 0, n_sm = 0, per_sm = 0;
+  if (!attr) {
     int dev = 0;
     DGOD_CUDA(cudaGetDevice(&dev));
     DGOD_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     DGOD_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    DGOD_CUDA(cudaFuncSetAttribute(msroi_bwd_tma_kernel<T, C, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdRing));
+    DGOD_CUDA(cudaFuncSetAttribute(msroi_bwd_tma_persistent_kernel<T, C, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdRing));
+    DGOD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msroi_bwd_tma_persistent_kernel<T, C, SR>, C, kBwdRing));
+    attr = true;
   }
-  const size_t need_ws = (size_t)g.B * sizeof(int);
-  const bool persistent = coop && roi_img_offsets && workspace && workspace_bytes >= need_ws && g.B > 1;
-  if (persistent) {
-    if (smem > attr_p) {
-      DGOD_CUDA(cudaFuncSetAttribute(msroi_bwd_tma_persistent_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_p = smem;
-    }
-    static int per_sm = 0, per_sm_c = 0;
-    if (per_sm_c != g.C) {
-      DGOD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msroi_bwd_tma_persistent_kernel<T>, g.C, smem));
-      per_sm_c = g.C;
-    }
-    if (per_sm >= 1) {
-      int* counters = (int*)workspace;
-      DGOD_CUDA(cudaMemsetAsync(counters, 0, need_ws, st));
-      const T* go = (const T*)grad_out;
-      RoiDev gg = g;
-      void* args[] = {(void*)&gg, (void*)&go, (void*)&rois, (void*)&roi_img_offsets, (void*)&counters};
-      DGOD_CUDA(cudaLaunchCooperativeKernel((const void*)msroi_bwd_tma_persistent_kernel<T>, dim3(per_sm * n_sm), dim3(g.C), args, smem, st));
-      g_launches.fetch_add(1, std::memory_order_relaxed);
-      return DGOD_OK;
-    }
+  const size_t need_ws = 2 * (size_t)g.B * sizeof(int);
+  if (coop && per_sm >= 1 && roi_img_offsets && workspace && workspace_bytes >= need_ws) {
+    int* counters = (int*)workspace;
+    DGOD_CUDA(cudaMemsetAsync(counters, 0, need_ws, st));
+    const T* go = (const T*)grad_out;
+    RoiDev gg = g;
+    void* args[] = {(void*)&gg, (void*)&go, (void*)&rois, (void*)&roi_img_offsets, (void*)&counters};
+    DGOD_CUDA(cudaLaunchCooperativeKernel((const void*)msroi_bwd_tma_persistent_kernel<T, C, SR>, dim3(per_sm * n_sm), dim3(C), args,
+                                          kBwdRing, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return DGOD_OK;
   }
   for (int l = 0; l < g.n_levels; ++l)
     DGOD_CUDA(cudaMemsetAsync(g.gfeat[l], 0, (size_t)g.B * g.C * g.H[l] * g.W[l] * sizeof(T), st));
   if (n_rois == 0) return DGOD_OK;
-  if (smem > attr) {
-    DGOD_CUDA(cudaFuncSetAttribute(msroi_bwd_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
-  msroi_bwd_tma_kernel<T><<<n_rois, g.C, smem, st>>>(g, (const T*)grad_out, rois, n_rois);
+  msroi_bwd_tma_kernel<T, C, SR><<<n_rois, C, kBwdRing, st>>>(g, (const T*)grad_out, rois, n_rois);
   DGOD_LAUNCHED();
   return DGOD_OK;
+}
+
+template <typename T>
+static int dispatch_bwd_tma(const RoiDev& g, const void* grad_out, const float* rois, int n_rois, const int32_t* offs,
+                            void* ws, size_t wsb, cudaStream_t st) {
+  if (g.C == 256)
+    return g.sr == 2 ? launch_bwd_tma<T, 256, 2>(g, grad_out, rois, n_rois, offs, ws, wsb, st)
+                     : launch_bwd_tma<T, 256, 1>(g, grad_out, rois, n_rois, offs, ws, wsb, st);
+  if (g.C == 128) return launch_bwd_tma<T, 128, 2>(g, grad_out, rois, n_rois, offs, ws, wsb, st);
+  return launch_bwd_tma<T, 64, 2>(g, grad_out, rois, n_rois, offs, ws, wsb, st);
 }
 
 int msroi_bwd_tma(const dgod_roi_config* cfg, const RoiDev& g, const void* grad_out, const float* rois, int n_rois,
@@ -496,9 +599,9 @@ int msroi_bwd_tma(const dgod_roi_config* cfg, const RoiDev& g, const void* grad_
   for (int l = 0; l < g.n_levels; ++l)
     if ((uintptr_t)g.gfeat[l] & 15) return DGOD_OK;
   *handled = 1;
-  if (cfg->dtype == DGOD_F32)
-    return launch_bwd_tma<float>(g, grad_out, rois, n_rois, roi_img_offsets, workspace, workspace_bytes, st);
-  return launch_bwd_tma<__nv_bfloat16>(g, grad_out, rois, n_rois, roi_img_offsets, workspace, workspace_bytes, st);
+  return cfg->dtype == DGOD_F32
+             ? dispatch_bwd_tma<float>(g, grad_out, rois, n_rois, roi_img_offsets, workspace, workspace_bytes, st)
+             : dispatch_bwd_tma<__nv_bfloat16>(g, grad_out, rois, n_rois, roi_img_offsets, workspace, workspace_bytes, st);
 }
 
 }  // namespace dgod

@@ -81,9 +81,14 @@ class DGFRCNN(nn.Module):
     `batch` = (images list, boxes list, labels list, domain tensor) like DGcommon.collate_fn."""
 
     def __init__(self, n_classes: int, batch_size: int, exp: str, reg_weights: Sequence[float], num_domains: int,
-                 min_size: int = 600, max_size: int = 1200):
+                 min_size: int = 600, max_size: int = 1200, batched_modes: bool = True):
         super().__init__()
         self.n_classes, self.batch_size, self.exp = n_classes, batch_size, exp
+        # Modes 2-4 of the reference run B separate batch-1 detector passes (DGFRCNN.py:165,177,190).
+        # Every term of those losses is per image (frozen BatchNorm, per-image RPN / RoI heads), so one
+        # batched pass + per-image slices of box_features / box_labels gives the same losses and
+        # gradients with 1/B of the launches (SURVEY.md §8f rank 2).  False = the reference's loop.
+        self.batched_modes = batched_modes
         self.reg_weights, self.num_domains = list(reg_weights), num_domains
         self.mode = 0
         self.sub_mode = 0
@@ -124,11 +129,49 @@ class DGFRCNN(nn.Module):
             self.sub_mode = 0
             self.mode = 0
 
+    def _instance_losses_batched(self, heads, domain: Tensor, own_domain: bool) -> Tensor:
+        """Per-(image, head) cross-entropy terms of modes 2-4 from ONE batched detector pass.
+        Every head scores every image's 512 RoI features; a device-side mask then keeps head
+        domain[i] for image i (own_domain) or all the other heads (mode 4) — no host read of the
+        domain ids.  Returns the mean over the kept terms (DGFRCNN.py:170,181,196)."""
+        feats = self.box_features                                           # [B*S, 1024]
+        B = len(self.box_labels)
+        labels = torch.stack(self.box_labels).reshape(-1)                   # [B*S]
+        S = labels.numel() // B
+        per = []
+        for head in heads:
+            ce = F.cross_entropy(head(feats), labels, reduction="none").view(B, S).mean(1)
+            per.append(ce)
+        per = torch.stack(per, dim=1)                                       # [B, D]
+        own = F.one_hot(domain.long(), len(heads)).to(per.dtype)
+        keep = own if own_domain else 1.0 - own
+        return (per * keep).sum() / keep.sum()
+
     def training_step(self, batch) -> Tensor:
         imgs, boxes, labels, domain = batch
         dev = imgs[0].device
         targets = [{"boxes": b.float(), "labels": l.long()} for b, l in zip(boxes, labels)]
         domain = domain.to(dev)
+        if self.batched_modes and self.mode >= 2:
+            if self.mode == 2:
+                for head in self.InsCls:
+                    for p in head.parameters():
+                        p.requires_grad = True
+                with torch.no_grad():
+                    self.detector(imgs, targets)
+                loss = self.reg_weights[4] * self._instance_losses_batched(self.InsCls, domain, True)
+            elif self.mode == 3:
+                self.detector(imgs, targets)
+                loss = self.reg_weights[3] * self._instance_losses_batched(self.InsClsPrime, domain, True)
+            else:
+                for head in self.InsCls:
+                    for p in head.parameters():
+                        p.requires_grad = False
+                self.detector(imgs, targets)
+                loss = self.reg_weights[4] * self._instance_losses_batched(self.InsCls, domain, False)
+                self.sub_mode = 0
+            self.mode = 0
+            return loss
         dom_list = domain.tolist() if self.mode >= 2 else None
         if self.mode == 0:
             det = self.detector(imgs, targets)
