@@ -62,7 +62,8 @@ SIGNATURES = {
     "dgod_rpn_workspace_bytes": (sz, [C.POINTER(RpnConfig)]),
     "dgod_rpn_proposals": (i32, [C.POINTER(RpnConfig), C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, vp, sz, vp]),
     "dgod_rpn_filter": (i32, [C.POINTER(RpnConfig), vp, vp, vp, vp, vp, vp, vp, sz, vp]),
-    "dgod_msroi_align_fwd": (i32, [C.POINTER(RoiConfig), C.POINTER(vp), vp, i32, vp, vp]),
+    "dgod_msroi_align_fwd_workspace_bytes": (sz, [i32]),
+    "dgod_msroi_align_fwd": (i32, [C.POINTER(RoiConfig), C.POINTER(vp), vp, i32, vp, vp, sz, vp]),
     "dgod_msroi_align_bwd_workspace_bytes": (sz, [i32]),
     "dgod_msroi_align_bwd": (i32, [C.POINTER(RoiConfig), vp, vp, i32, vp, C.POINTER(vp), i32, vp, sz, vp]),
     "dgod_box_decode": (i32, [vp, vp, i32, i32, f32, f32, f32, f32, f32, vp, vp]),

@@ -168,11 +168,11 @@ size_t msroi_bwd_workspace(int n_rois);
 int msroi_bwd_red(const dgod_roi_config* cfg, const RoiDev& g, const void* grad_out, const float* rois,
                   int n_rois, cudaStream_t st, int* handled);
 // TMA paths (roi_align_tma.cu): channels_last, 7x7 bins, sampling ratio 1..2
-int msroi_fwd_tma(const dgod_roi_config* cfg, const RoiDev& g, const float* rois, int n_rois, void* out,
-                  cudaStream_t st, int* handled);
+int msroi_fwd_tma(const dgod_roi_config* cfg, const RoiDev& g, const float* rois, int n_rois, void* out, void* workspace,
+                  size_t workspace_bytes, cudaStream_t st, int* handled);
 int msroi_bwd_tma(const dgod_roi_config* cfg, const RoiDev& g, const void* grad_out, const float* rois, int n_rois,
-                  const int32_t* roi_img_offsets, void* workspace, size_t workspace_bytes, cudaStream_t st,
-                  int* handled);
+                  void* workspace, size_t workspace_bytes, cudaStream_t st, int* handled);
+size_t msroi_tma_workspace(int n_rois);
 
 // DGOD_FWD_ALGO=1 keeps the forward on the table-driven kernel (A/B measurements); default: TMA path first.
 static int fwd_algo_from_env() {
@@ -188,9 +188,11 @@ static int fwd_algo_from_env() {
 
 using namespace dgod;
 
+extern "C" size_t dgod_msroi_align_fwd_workspace_bytes(int n_rois) { return msroi_tma_workspace(n_rois); }
+
 extern "C" int dgod_msroi_align_fwd(const dgod_roi_config* cfg, const void* const* feats,
-                                    const float* rois, int n_rois, void* out,
-                                    dgod_stream_t stream) {
+                                    const float* rois, int n_rois, void* out, void* workspace,
+                                    size_t workspace_bytes, dgod_stream_t stream) {
   RoiDev g;
   int rc = fill_roi_dev(cfg, g);
   if (rc) return rc;
@@ -204,7 +206,7 @@ extern "C" int dgod_msroi_align_fwd(const dgod_roi_config* cfg, const void* cons
   cudaStream_t st = (cudaStream_t)stream;
   int handled = 0;
   if (fwd_algo_from_env() == 0) {
-    rc = msroi_fwd_tma(cfg, g, rois, n_rois, out, st, &handled);
+    rc = msroi_fwd_tma(cfg, g, rois, n_rois, out, workspace, workspace_bytes, st, &handled);
     if (rc || handled) return rc;
   }
   rc = msroi_fwd_fast(cfg, g, rois, n_rois, out, st, &handled);
@@ -220,7 +222,10 @@ extern "C" int dgod_msroi_align_fwd(const dgod_roi_config* cfg, const void* cons
   return DGOD_OK;
 }
 
-extern "C" size_t dgod_msroi_align_bwd_workspace_bytes(int n_rois) { return msroi_bwd_workspace(n_rois); }
+extern "C" size_t dgod_msroi_align_bwd_workspace_bytes(int n_rois) {
+  const size_t a = msroi_bwd_workspace(n_rois), b = msroi_tma_workspace(n_rois);
+  return a > b ? a : b;
+}
 
 extern "C" int dgod_msroi_align_bwd(const dgod_roi_config* cfg, const void* grad_out,
                                     const float* rois, int n_rois,
@@ -246,7 +251,7 @@ extern "C" int dgod_msroi_align_bwd(const dgod_roi_config* cfg, const void* grad
   // on NCHW) and bf16 gradients the deterministic tile gather (fp32 accumulation, one rounding).
   if (algo == 0 || algo == 3) {
     int handled = 0;
-    rc = msroi_bwd_tma(cfg, g, grad_out, rois, n_rois, roi_img_offsets, workspace, workspace_bytes, st, &handled);
+    rc = msroi_bwd_tma(cfg, g, grad_out, rois, n_rois, workspace, workspace_bytes, st, &handled);
     if (rc || handled) return rc;
     DGOD_REQUIRE(algo == 0, "roi_align: the TMA backward does not support this configuration");
   }

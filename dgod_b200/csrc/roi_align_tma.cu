@@ -4,36 +4,43 @@
 //
 // In NHWC a row of an RoI's footprint — pixels x0..x1 of feature row y, all C channels — is ONE
 // contiguous span of (x1-x0+1)*C*s bytes.  Both kernels move whole footprint rows with the bulk
-// async-copy engine instead of issuing per-tap loads / per-tap reductions from the SM lanes:
+// async-copy engine instead of issuing per-tap loads / per-tap reductions from the SM lanes.
 //
-//   forward   cp.async.bulk global->shared (mbarrier complete_tx) streams the live footprint rows
-//             through a multi-stage ring (up to 8 rows in flight per CTA); the pooled [C][49]
-//             block leaves as one bulk store.
-//   backward  each footprint row is assembled in shared memory and added to the gradient map by
-//             ONE cp.reduce.async.bulk (SASS UBLKRED) — the L2 does the read-modify-write.  The
-//             previous kernel issued 16 RED per output element and was bound by the SM's RED
-//             issue rate (~1.3 cycles per lane).
+// Three kernels:
+//   msroi_plan_kernel   one warp per RoI: level mapping, sampling taps (the same axis_tap() the
+//                       exact kernels use, i.e. TV's out-of-range skip rule and border clamp), the
+//                       compact list of live feature rows, the separable weight tables.  The result
+//                       is a 3.3 KB "plan" record per RoI in the caller's workspace, so the
+//                       streaming kernels below do no per-RoI arithmetic at all.
+//   msroi_fwd_tma       one CTA per RoI, warp-specialised.  A producer lane bulk-loads the plan and
+//                       streams the live footprint rows through a ring of up to 8 stages
+//                       (cp.async.bulk global->shared, mbarrier complete_tx).  C/2 consumer threads
+//                       own two adjacent channels each (packed fp32 FFMA2), keep the 49 pooled
+//                       values of both in registers and hand stages back through per-stage
+//                       mbarriers — warps never wait for each other inside an RoI.  The pooled
+//                       [C][49] block is staged in shared memory and leaves as ONE bulk store.
+//   msroi_bwd_tma       persistent, cooperative launch.  The producer prefetches the RoI's
+//                       [C][49] gradient block; consumers assemble each live footprint row in shared
+//                       memory and add it to the gradient map with ONE cp.reduce.async.bulk (SASS
+//                       UBLKRED): the L2 does the read-modify-write.  (The per-tap kernel issued 16
+//                       RED per output element and was bound by the SM's RED issue rate, ~1.3
+//                       cycles per lane.)  Every CTA zero-fills its share of image b+1 before it
+//                       starts on image b's RoIs and an RoI of image b waits for zero_done[b], so
+//                       the gradient maps need no memset and the zero lines are still dirty in L2
+//                       when the reductions arrive.
 //
 // Arithmetic: bilinear pooling is separable.  With A_y[y][ph] = sum over the sampling rows of bin
-// ph of the weight they put on feature row y (and the per-sample column taps likewise),
+// ph of the weight they put on feature row y (and the column taps likewise),
 //       out[c][ph][pw]  = sum_y A_y[y][ph] * ( sum_{sx in pw} h*f[y][xlo][c] + l*f[y][xhi][c] ) / count
 //       grad_f[y][x][c] = sum_pw A_x[x][pw] * ( sum_ph A_y[y][ph] * g[c][ph][pw] ) / count
-// One thread owns one channel and keeps the 49 pooled values / gradients of that channel in
-// registers; the tables are built once per RoI in shared memory and read as warp broadcasts.  A
-// sampling axis has at most 2*PH*sr = 28 live rows (columns) however large the RoI is, so rows
-// are visited through a compact list; RoIs whose column span exceeds 32 pixels switch from one
-// span per row to one 2-pixel slot per sample ("slot mode").  Out-of-range samples (TV's skip
-// rule) and the border clamp come from the same axis_tap() the exact kernels use.  The summation
-// order differs from the CPU kernel's sample-by-sample order: results agree to fp32 rounding
-// (tests: 1e-5 relative), not bitwise.
+// A sampling axis has at most 2*PH*sr = 28 live rows (columns) however large the RoI is; RoIs whose
+// column span exceeds 28 pixels switch from one span per row to one 2-pixel slot per sample ("slot
+// mode").  The summation order differs from the CPU kernel's sample-by-sample order: results agree
+// to fp32 rounding (tests: 1e-5 relative), not bitwise.
 //
-// Roofline: HBM.  Forward reads every touched feature line once (the image's maps stay in the
-// 126 MB L2 while its RoIs are in flight) and writes K*C*49*s.  Backward reads K*C*49*s and
-// writes every gradient line once: a persistent cooperative grid zero-fills image b+1 while it
-// reduces image b's RoIs (per-image completion counters, no grid-wide barrier), so the
-// read-modify-write traffic stays in L2 and DRAM sees each line once.  Measured on B200
-// (tools/microbench/tma_bulk.cu): bulk reduce 5.8 TB/s into an L2-resident region, 3.0 TB/s into
-// a 400 MB one (DRAM read-modify-write); bulk load up to 17 TB/s on L2 hits.
+// Roofline: HBM (SURVEY.md §8d byte model).  Measured on B200 (tools/microbench/tma_bulk.cu): bulk
+// reduce 5.8 TB/s into an L2-resident region, 3.0 TB/s into a 400 MB one (DRAM read-modify-write);
+// bulk load up to 17 TB/s on L2 hits; bulk store 7.3 TB/s.
 #include "roi_common.cuh"
 
 namespace dgod {
@@ -42,10 +49,10 @@ constexpr int kP = 7;                  // pooled size handled by these kernels (
 constexpr int kNB = kP * kP;
 constexpr int kMaxSamp = 14;           // samples per axis (kP * sampling_ratio, sr <= 2)
 constexpr int kMaxLive = 2 * kMaxSamp; // live rows / columns per axis
-constexpr int kSpanMax = 32;           // widest column span moved as one piece per row
-constexpr int kStagesMax = 8;
-constexpr int kFwdRing = 96 * 1024;    // forward: row ring (also the output staging block)
-constexpr int kBwdRing = 64 * 1024;    // backward: gradient-block staging, then the row buffers
+constexpr int kSpanMax = 28;           // widest column span moved as one piece per row
+constexpr int kPlanBufBwd = 2;
+constexpr int kCounterBytes = 4096;    // head of the workspace: zero_done[batch] (backward)
+constexpr int kSmemBudget = 112 * 1024;   // static + dynamic per CTA for 2 CTAs per SM
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -56,6 +63,9 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned coun
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   asm volatile(
@@ -89,28 +99,90 @@ template <> __device__ __forceinline__ void bulk_reduce_add<__nv_bfloat16>(void*
                "r"(smem_u32(smem_src)), "r"(bytes)
                : "memory");
 }
+// L2 eviction-priority hints: streamed-once data (plans, gradient blocks, pooled output) is marked
+// evict_first so that it does not push the re-used maps (features / gradient maps of the image in
+// flight, marked evict_last) out of the L2.
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_load_hint(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar,
+                                               unsigned long long policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_hint(void* gmem_dst, const void* smem_src, unsigned bytes, unsigned long long policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n" ::"l"(gmem_dst),
+               "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy)
+               : "memory");
+}
+template <typename T> __device__ __forceinline__ void bulk_reduce_add_hint(void* gmem_dst, const void* smem_src, unsigned bytes,
+                                                                           unsigned long long policy);
+template <> __device__ __forceinline__ void bulk_reduce_add_hint<float>(void* gmem_dst, const void* smem_src, unsigned bytes,
+                                                                        unsigned long long policy) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.L2::cache_hint.add.f32 [%0], [%1], %2, %3;\n" ::"l"(gmem_dst),
+               "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy)
+               : "memory");
+}
+template <> __device__ __forceinline__ void bulk_reduce_add_hint<__nv_bfloat16>(void* gmem_dst, const void* smem_src, unsigned bytes,
+                                                                                unsigned long long policy) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.L2::cache_hint.add.noftz.bf16 [%0], [%1], %2, %3;\n" ::"l"(gmem_dst),
+               "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void st_zero16_hint(void* p, unsigned long long policy) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %1, %1, %1}, %2;\n" ::"l"(p), "r"(0u), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;\n" ::"n"(N) : "memory"); }
 
-// ---------------------------------------------------------------- per-RoI tables (shared memory)
-struct TapEntry { unsigned off_lo, off_hi; float h, l; };   // byte offsets inside a row buffer + weights
+// ---------------------------------------------------------------- the per-RoI plan
+struct alignas(16) ColTap { unsigned off_lo, off_hi, pad0, pad1; float hx, hy, lx, ly; };   // row-buffer byte offsets; (h,h), (l,l)
 
-struct alignas(16) RoiSmem {
-  alignas(16) float ay[kMaxLive][8];   // dense A_y of the live rows (list order)
-  alignas(16) float ax[kSpanMax][8];   // backward, span mode: dense A_x of the span's columns
-  alignas(16) TapEntry xs[kMaxSamp];   // column taps of every sample (row-buffer byte offsets)
-  alignas(8) unsigned long long full[kStagesMax];
-  alignas(8) unsigned long long gbar;  // backward: gradient block landed
+struct alignas(128) RoiPlan {
+  // header (64 B)
+  int n_rows;            // live feature rows (0: nothing to do — RoI unusable or entirely out of range)
+  int row_px;            // pixels per row buffer: the span, or 2 * n_slots in slot mode
+  int slot_mode, n_slots;
+  int level, batch;
+  int x_first;           // span mode: first column of the span
+  float inv_count;       // 1 / (sr*sr)
+  int pad[8];
+  // lists (128 B)
+  short rows[kMaxLive];                 // live feature rows, ascending
+  short slot_x[kMaxSamp];               // slot mode: first pixel of sample s
+  signed char slot_of[kMaxSamp + 2];    // slot mode: compact slot index of a valid sample, -1 otherwise
+  unsigned char slot_two[kMaxSamp + 2]; // slot mode: the slot holds two pixels (xhi != xlo)
+  unsigned char pad2[12];
+  // tables
+  ColTap xs[kMaxSamp];                  // 448 B   column taps of every sample
+  float2 ay2[kMaxLive][8];              // 1792 B  (a,a) of the live rows, list order, unscaled
+  float ax[kSpanMax][8];                // 896 B   backward, span mode: dense A_x of the span's columns
+};
+static_assert(sizeof(RoiPlan) % 128 == 0, "plans are moved with bulk copies");
+constexpr int kPlanFwdBytes = (int)offsetof(RoiPlan, ax);       // the forward kernel loads this prefix
+constexpr int kPlanBwdBytes = (int)sizeof(RoiPlan);
+static_assert(kPlanFwdBytes % 16 == 0, "bulk copy granularity");
+
+// ---------------------------------------------------------------- plan kernel (one warp per RoI)
+struct PlanScratch {
   RoiGeom geo;
   short ylo[kMaxSamp], yhi[kMaxSamp], xlo[kMaxSamp], xhi[kMaxSamp];
   float yl[kMaxSamp], yh[kMaxSamp], xl[kMaxSamp], xh[kMaxSamp];   // both zero: sample skipped
-  short rows[kMaxLive];                // live feature rows, ascending
-  short slot_of[kMaxSamp];             // slot mode: compact slot index of a valid sample (-1 otherwise)
-  int n_rows, x_first, x_last, n_slots, slot_mode;
-  int next_k;
+  short rows[kMaxLive];
+  short slot_of[kMaxSamp];
+  int n_rows, x_first, x_last, n_slots;
 };
 
-// Lane `lane` < n fills sample `lane` of one axis.
 __device__ __forceinline__ void fill_axis_samples(short* lo, short* hi, float* l, float* h, int lane, int n, int sr,
                                                   float start, float bin, int size) {
   if (lane < n) {
@@ -134,186 +206,251 @@ __device__ __forceinline__ float axis_weight(const short* lo, const short* hi, c
   return w;
 }
 
-// Warp 0: compact, ascending list of the rows that receive weight; warp 1: column extent, slot map.
-// Call with all threads after the sample tables are visible; ends with the lists visible.
-template <int SR>
-__device__ __forceinline__ void build_lists(RoiSmem& t, int tid) {
-  constexpr int NS = kP * SR;
-  const int lane = tid & 31;
-  if (tid < 32) {
-    const int s = lane >> 1, is_hi = lane & 1;
-    bool valid = false;
-    int r = 0;
-    if (s < NS) {
-      const bool live = t.yh[s] != 0.f || t.yl[s] != 0.f;
-      valid = live && (is_hi ? (t.yl[s] != 0.f && t.yhi[s] != t.ylo[s]) : true);
-      r = is_hi ? t.yhi[s] : t.ylo[s];
+constexpr int kPlanWarps = 4;
+
+__global__ void __launch_bounds__(kPlanWarps * 32)
+msroi_plan_kernel(const RoiDev g, const float* __restrict__ rois, int n_rois, RoiPlan* __restrict__ plans, int pix_bytes,
+                  int want_ax) {
+  __shared__ PlanScratch scratch[kPlanWarps];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int k = blockIdx.x * kPlanWarps + w;
+  if (k >= n_rois) return;
+  PlanScratch& t = scratch[w];
+  RoiPlan& P = plans[k];
+  const int sr = g.sr, ns = kP * sr;
+  if (lane == 0) t.geo = roi_geometry(g, rois + (size_t)k * 5);
+  __syncwarp();
+  const RoiGeom r = t.geo;
+  const bool usable = r.batch >= 0 && r.batch < g.B;
+  int n_rows = 0;
+  if (usable) {
+    fill_axis_samples(t.ylo, t.yhi, t.yl, t.yh, lane, ns, sr, r.start_h, r.bin_h, r.H);
+    fill_axis_samples(t.xlo, t.xhi, t.xl, t.xh, lane, ns, sr, r.start_w, r.bin_w, r.W);
+    __syncwarp();
+    {  // compact, ascending list of the feature rows that receive weight
+      const int s = lane >> 1, is_hi = lane & 1;
+      bool valid = false;
+      int row = 0;
+      if (s < ns) {
+        const bool live = t.yh[s] != 0.f || t.yl[s] != 0.f;
+        valid = live && (is_hi ? (t.yl[s] != 0.f && t.yhi[s] != t.ylo[s]) : true);
+        row = is_hi ? t.yhi[s] : t.ylo[s];
+      }
+      const unsigned same = __match_any_sync(0xffffffffu, valid ? row : (0x10000 + lane));
+      const bool first = valid && (__ffs(same) - 1 == lane);
+      int rank = 0;
+      for (int j = 0; j < 2 * ns; ++j) {
+        const int rj = __shfl_sync(0xffffffffu, row, j);
+        const int fj = __shfl_sync(0xffffffffu, (int)first, j);
+        rank += (fj && rj < row) ? 1 : 0;
+      }
+      if (first) t.rows[rank] = (short)row;
+      const unsigned m = __ballot_sync(0xffffffffu, first);
+      if (lane == 0) t.n_rows = __popc(m);
     }
-    const unsigned same = __match_any_sync(0xffffffffu, valid ? r : (0x10000 + lane));
-    const bool first = valid && (__ffs(same) - 1 == lane);
-    int rank = 0;
+    {  // column extent of the weighted taps, compact slot index of every valid sample
+      int lo = 0x7fffffff, hi = -1;
+      bool valid = false;
+      if (lane < ns) {
+        valid = t.xh[lane] != 0.f || t.xl[lane] != 0.f;
+        if (valid) { lo = t.xlo[lane]; hi = (t.xl[lane] != 0.f) ? t.xhi[lane] : t.xlo[lane]; }
+      }
+      const unsigned vm = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
-    for (int j = 0; j < 2 * NS; ++j) {
-      const int rj = __shfl_sync(0xffffffffu, r, j);
-      const int fj = __shfl_sync(0xffffffffu, (int)first, j);
-      rank += (fj && rj < r) ? 1 : 0;
+      for (int d = 16; d >= 1; d >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+      }
+      if (lane < ns) t.slot_of[lane] = valid ? (short)__popc(vm & ((1u << lane) - 1u)) : (short)-1;
+      if (lane == 0) { t.x_first = lo; t.x_last = hi; t.n_slots = __popc(vm); }
     }
-    if (first) t.rows[rank] = (short)r;
-    const unsigned m = __ballot_sync(0xffffffffu, first);
-    if (lane == 0) t.n_rows = __popc(m);
-  } else if (tid < 64) {
-    int lo = 0x7fffffff, hi = -1;
-    bool valid = false;
-    if (lane < NS) {
-      valid = t.xh[lane] != 0.f || t.xl[lane] != 0.f;
-      if (valid) { lo = t.xlo[lane]; hi = (t.xl[lane] != 0.f) ? t.xhi[lane] : t.xlo[lane]; }
+    __syncwarp();
+    n_rows = (t.x_first <= t.x_last) ? t.n_rows : 0;
+  }
+  const int x_first = n_rows ? t.x_first : 0;
+  const int span = n_rows ? (t.x_last - x_first + 1) : 0;
+  const int slot_mode = span > kSpanMax;
+  const int n_slots = n_rows ? t.n_slots : 0;
+  const int row_px = slot_mode ? 2 * n_slots : span;
+  if (lane == 0) {
+    P.n_rows = n_rows; P.row_px = row_px; P.slot_mode = slot_mode; P.n_slots = n_slots;
+    P.level = r.level; P.batch = usable ? r.batch : 0; P.x_first = x_first;
+    P.inv_count = 1.f / r.count;           // count = sr*sr: a power of two
+  }
+  if (!n_rows) return;
+  if (lane < kMaxLive) P.rows[lane] = lane < n_rows ? t.rows[lane] : (short)0;
+  if (lane < kMaxSamp) {
+    const bool in = lane < ns;
+    const bool valid = in && (t.xh[lane] != 0.f || t.xl[lane] != 0.f);
+    const bool two = valid && t.xhi[lane] != t.xlo[lane];
+    P.slot_x[lane] = valid ? t.xlo[lane] : (short)0;
+    P.slot_of[lane] = (signed char)(valid ? t.slot_of[lane] : -1);
+    P.slot_two[lane] = (unsigned char)two;
+    ColTap e;
+    e.hx = e.hy = in ? t.xh[lane] : 0.f;
+    e.lx = e.ly = in ? t.xl[lane] : 0.f;
+    e.pad0 = e.pad1 = 0u;
+    if (!valid) {
+      e.off_lo = e.off_hi = 0u;          // weights are zero; offset 0 is always a loaded pixel
+    } else if (slot_mode) {
+      e.off_lo = (unsigned)t.slot_of[lane] * 2u * pix_bytes;
+      e.off_hi = e.off_lo + (two ? (unsigned)pix_bytes : 0u);
+    } else {
+      e.off_lo = (unsigned)(t.xlo[lane] - x_first) * pix_bytes;
+      e.off_hi = (unsigned)(t.xhi[lane] - x_first) * pix_bytes;
     }
-    const unsigned vm = __ballot_sync(0xffffffffu, valid);
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
-      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
-    }
-    if (lane < NS) t.slot_of[lane] = valid ? (short)__popc(vm & ((1u << lane) - 1u)) : (short)-1;
-    if (lane == 0) {
-      t.x_first = lo;
-      t.x_last = hi;
-      t.n_slots = __popc(vm);
-      t.slot_mode = (hi - lo + 1) > kSpanMax;
+    P.xs[lane] = e;
+  }
+  for (int e = lane; e < kMaxLive * 8; e += 32) {
+    const int i = e >> 3, p = e & 7;
+    const float a = (i < n_rows && p < kP) ? axis_weight(t.ylo, t.yhi, t.yl, t.yh, t.rows[i], p, sr) : 0.f;
+    P.ay2[i][p] = make_float2(a, a);
+  }
+  if (want_ax && !slot_mode) {
+    for (int e = lane; e < kSpanMax * 8; e += 32) {
+      const int i = e >> 3, p = e & 7;
+      P.ax[i][p] = (i < span && p < kP) ? axis_weight(t.xlo, t.xhi, t.xl, t.xh, x_first + i, p, sr) : 0.f;
     }
   }
-  __syncthreads();
 }
 
-template <typename T> __device__ __forceinline__ float ld_elem(const unsigned char* p);
-template <> __device__ __forceinline__ float ld_elem<float>(const unsigned char* p) { return *reinterpret_cast<const float*>(p); }
-template <> __device__ __forceinline__ float ld_elem<__nv_bfloat16>(const unsigned char* p) {
-  return __uint_as_float((unsigned)(*reinterpret_cast<const unsigned short*>(p)) << 16);
+template <typename T> __device__ __forceinline__ float2 ld_pair(const unsigned char* p);
+template <> __device__ __forceinline__ float2 ld_pair<float>(const unsigned char* p) { return *reinterpret_cast<const float2*>(p); }
+template <> __device__ __forceinline__ float2 ld_pair<__nv_bfloat16>(const unsigned char* p) {
+  const unsigned u = *reinterpret_cast<const unsigned*>(p);
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+template <typename T> __device__ __forceinline__ void st_pair(unsigned char* p, float2 v);
+template <> __device__ __forceinline__ void st_pair<float>(unsigned char* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+template <> __device__ __forceinline__ void st_pair<__nv_bfloat16>(unsigned char* p, float2 v) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y);
 }
 
 // ================================================================================================
 // Forward
 // ================================================================================================
+// One CTA per RoI (two resident per SM), warp-specialised: a producer lane streams the RoI's live
+// rows through a ring of up to 8 stages; C/2 consumer threads own two adjacent channels each.
+// (A persistent variant that packed the rows of consecutive RoIs into one ring measured slower on
+// B200: with the pooled block staged separately the ring shrank to ~3 rows in flight per CTA, and the
+// loads are latency-bound.)  Here the staging block aliases the ring once the rows are consumed.
+constexpr int kStagesMax = 8;
+
+struct alignas(16) FwdSync {
+  alignas(8) unsigned long long plan_full;
+  alignas(8) unsigned long long full[kStagesMax], empty[kStagesMax];
+};
+
+template <typename T, int C> struct FwdCfg {
+  static constexpr int kStaging = C * kNB * (int)sizeof(T);                       // pooled block of one RoI
+  static constexpr int kRing = ((kSmemBudget - kPlanFwdBytes - (int)sizeof(FwdSync) - 256) / 1024) * 1024;
+  static constexpr int kSmem = kRing + kPlanFwdBytes;
+  static_assert(kRing >= kStaging && kRing >= 3 * kSpanMax * C * (int)sizeof(T), "ring: staging alias and >= 3 widest rows");
+};
+
 template <typename T, int C, int SR>
-__global__ void __launch_bounds__(C, (C == 256) ? 2 : 4)
-msroi_fwd_tma_kernel(const RoiDev g, const float* __restrict__ rois, int n_rois, T* __restrict__ out) {
+__global__ void __launch_bounds__(C / 2 + 32, 2)
+msroi_fwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, int n_rois, T* __restrict__ out) {
   constexpr int NS = kP * SR;
+  constexpr int NC = C / 2;                          // consumer threads
   constexpr int PIX = C * (int)sizeof(T);            // bytes per pixel
-  extern __shared__ __align__(128) unsigned char ring[];
-  __shared__ RoiSmem t;
+  constexpr int RING = FwdCfg<T, C>::kRing;
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* ring = smem;                        // row stages, then the pooled block [C][49]
+  const RoiPlan& P = *reinterpret_cast<const RoiPlan*>(smem + RING);
+  __shared__ FwdSync f;
   const int tid = threadIdx.x;
   const int k = blockIdx.x;
 
   if (tid == 0) {
-    t.geo = roi_geometry(g, rois + (size_t)k * 5);
+    mbar_init(&f.plan_full, 1);
 #pragma unroll
-    for (int i = 0; i < kStagesMax; ++i) mbar_init(&t.full[i], 1);
+    for (int i = 0; i < kStagesMax; ++i) {
+      mbar_init(&f.full[i], 1);
+      mbar_init(&f.empty[i], NC / 32);
+    }
     mbar_fence_init();
+    mbar_expect_tx(&f.plan_full, kPlanFwdBytes);
+    bulk_load_hint(smem + RING, plans + k, kPlanFwdBytes, &f.plan_full, policy_evict_first());
   }
   __syncthreads();
-  const RoiGeom r = t.geo;
-  const bool usable = r.batch >= 0 && r.batch < g.B;
-  if (usable) {
-    if (tid < 32) fill_axis_samples(t.ylo, t.yhi, t.yl, t.yh, tid, NS, SR, r.start_h, r.bin_h, r.H);
-    else if (tid < 64) fill_axis_samples(t.xlo, t.xhi, t.xl, t.xh, tid - 32, NS, SR, r.start_w, r.bin_w, r.W);
-  }
-  __syncthreads();
-
-  float acc[kNB];
+  mbar_wait(&f.plan_full, 0u);
+  const int n_rows = P.n_rows;
+  const float inv = P.inv_count;
+  float2 acc[kNB];
 #pragma unroll
-  for (int i = 0; i < kNB; ++i) acc[i] = 0.f;
+  for (int i = 0; i < kNB; ++i) acc[i] = make_float2(0.f, 0.f);
 
-  if (usable) {
-    build_lists<SR>(t, tid);
-    const int n_rows = t.n_rows;
-    if (n_rows > 0 && t.x_first <= t.x_last) {
-      const int x_first = t.x_first, slot_mode = t.slot_mode;
-      const int row_px = slot_mode ? 2 * t.n_slots : (t.x_last - x_first + 1);
-      const unsigned row_bytes = (unsigned)row_px * PIX;              // multiple of 128
-      const int n_stage = min(kStagesMax, kFwdRing / (int)row_bytes);   // >= 3 (row_bytes <= 32 KB)
-      // tables: A_y of the live rows, column taps as byte offsets into a row buffer
-      for (int e = tid; e < kMaxLive * 8; e += C) {
-        const int i = e >> 3, p = e & 7;
-        t.ay[i][p] = (i < n_rows && p < kP) ? axis_weight(t.ylo, t.yhi, t.yl, t.yh, t.rows[i], p, SR) : 0.f;
-      }
-      if (tid < NS) {
-        TapEntry e;
-        const bool valid = t.xh[tid] != 0.f || t.xl[tid] != 0.f;
-        e.h = t.xh[tid];
-        e.l = t.xl[tid];
-        if (!valid) {
-          e.off_lo = e.off_hi = 0u;      // weights are zero; offset 0 is always a loaded pixel
-        } else if (slot_mode) {
-          e.off_lo = (unsigned)t.slot_of[tid] * 2u * PIX;
-          e.off_hi = e.off_lo + ((t.xhi[tid] != t.xlo[tid]) ? PIX : 0u);
-        } else {
-          e.off_lo = (unsigned)(t.xlo[tid] - x_first) * PIX;
-          e.off_hi = (unsigned)(t.xhi[tid] - x_first) * PIX;
-        }
-        t.xs[tid] = e;
-      }
-      __syncthreads();
-      const T* __restrict__ img = reinterpret_cast<const T*>(g.feat[r.level]) + (size_t)r.batch * r.H * r.W * C;
-      auto issue_row = [&](int i) {      // thread 0 only
-        const int st = i % n_stage;
-        const size_t y = (size_t)t.rows[i];
-        unsigned char* dst = ring + (size_t)st * row_bytes;
-        if (!slot_mode) {
-          mbar_expect_tx(&t.full[st], row_bytes);
-          bulk_load(dst, img + (y * r.W + x_first) * C, row_bytes, &t.full[st]);
-        } else {
-          unsigned total = 0;
-          for (int s = 0; s < NS; ++s)
-            if (t.slot_of[s] >= 0) total += (t.xhi[s] != t.xlo[s]) ? 2u * PIX : (unsigned)PIX;
-          mbar_expect_tx(&t.full[st], total);
-          for (int s = 0; s < NS; ++s)
-            if (t.slot_of[s] >= 0)
-              bulk_load(dst + (size_t)t.slot_of[s] * 2 * PIX, img + (y * r.W + t.xlo[s]) * C,
-                        (t.xhi[s] != t.xlo[s]) ? 2u * PIX : (unsigned)PIX, &t.full[st]);
-        }
-      };
-      if (tid == 0)
-        for (int i = 0; i < min(n_stage, n_rows); ++i) issue_row(i);
+  if (n_rows) {
+    const unsigned row_bytes = (unsigned)P.row_px * PIX;                // multiple of 128, <= 28 KB
+    const int n_stage = min(kStagesMax, RING / (int)row_bytes);        // >= 3
+    if (tid == NC) {
+      // ---------------- producer lane
+      const int slot_mode = P.slot_mode, W = g.W[P.level];
+      const T* __restrict__ img = reinterpret_cast<const T*>(g.feat[P.level]) + (size_t)P.batch * g.H[P.level] * W * C;
+      unsigned slot_total = 0;
+      if (slot_mode)
+        for (int sx = 0; sx < NS; ++sx)
+          if (P.slot_of[sx] >= 0) slot_total += P.slot_two[sx] ? 2u * PIX : (unsigned)PIX;
+      const T* __restrict__ span0 = img + (size_t)P.x_first * C;
+      const unsigned long long keep = policy_evict_last();      // the image's maps are re-read by its other RoIs
       for (int i = 0; i < n_rows; ++i) {
         const int st = i % n_stage;
-        mbar_wait(&t.full[st], (unsigned)(i / n_stage) & 1u);
-        const unsigned char* __restrict__ row = ring + (size_t)st * row_bytes + tid * (int)sizeof(T);
-        float rx[kP];
-#pragma unroll
-        for (int p = 0; p < kP; ++p) rx[p] = 0.f;
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-          const uint4 e = *reinterpret_cast<const uint4*>(&t.xs[s]);
-          const float v0 = ld_elem<T>(row + e.x), v1 = ld_elem<T>(row + e.y);
-          rx[s / SR] = fmaf(__uint_as_float(e.w), v1, fmaf(__uint_as_float(e.z), v0, rx[s / SR]));
+        if (i >= n_stage) mbar_wait(&f.empty[st], (unsigned)(i / n_stage - 1) & 1u);
+        const size_t yw = (size_t)P.rows[i] * W;
+        unsigned char* dst = ring + (size_t)st * row_bytes;
+        if (!slot_mode) {
+          mbar_expect_tx(&f.full[st], row_bytes);
+          bulk_load_hint(dst, span0 + yw * C, row_bytes, &f.full[st], keep);
+        } else {
+          mbar_expect_tx(&f.full[st], slot_total);
+          for (int sx = 0; sx < NS; ++sx)
+            if (P.slot_of[sx] >= 0)
+              bulk_load_hint(dst + (size_t)P.slot_of[sx] * 2 * PIX, img + (yw + P.slot_x[sx]) * C,
+                             P.slot_two[sx] ? 2u * PIX : (unsigned)PIX, &f.full[st], keep);
         }
-        const float4 a0 = *reinterpret_cast<const float4*>(&t.ay[i][0]);
-        const float4 a1 = *reinterpret_cast<const float4*>(&t.ay[i][4]);
+      }
+    } else if (tid < NC) {
+      // ---------------- consumers: thread owns channels 2*tid, 2*tid+1
+      for (int i = 0; i < n_rows; ++i) {
+        const int st = i % n_stage;
+        mbar_wait(&f.full[st], (unsigned)(i / n_stage) & 1u);
+        const unsigned char* __restrict__ row = ring + (size_t)st * row_bytes + tid * 2 * (int)sizeof(T);
+        float2 rx[kP];
 #pragma unroll
-        for (int pw = 0; pw < kP; ++pw) {
-          acc[0 * kP + pw] = fmaf(a0.x, rx[pw], acc[0 * kP + pw]);
-          acc[1 * kP + pw] = fmaf(a0.y, rx[pw], acc[1 * kP + pw]);
-          acc[2 * kP + pw] = fmaf(a0.z, rx[pw], acc[2 * kP + pw]);
-          acc[3 * kP + pw] = fmaf(a0.w, rx[pw], acc[3 * kP + pw]);
-          acc[4 * kP + pw] = fmaf(a1.x, rx[pw], acc[4 * kP + pw]);
-          acc[5 * kP + pw] = fmaf(a1.y, rx[pw], acc[5 * kP + pw]);
-          acc[6 * kP + pw] = fmaf(a1.z, rx[pw], acc[6 * kP + pw]);
+        for (int p = 0; p < kP; ++p) rx[p] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int sx = 0; sx < NS; ++sx) {
+          const uint2 o = *reinterpret_cast<const uint2*>(&P.xs[sx].off_lo);
+          const float4 w = *reinterpret_cast<const float4*>(&P.xs[sx].hx);
+          const float2 v0 = ld_pair<T>(row + o.x), v1 = ld_pair<T>(row + o.y);
+          rx[sx / SR] = __ffma2_rn(make_float2(w.z, w.w), v1, __ffma2_rn(make_float2(w.x, w.y), v0, rx[sx / SR]));
         }
-        __syncthreads();                    // everyone is done with stage st: it may be refilled
-        if (tid == 0 && i + n_stage < n_rows) issue_row(i + n_stage);
+#pragma unroll
+        for (int ph = 0; ph < kP; ++ph) {
+          const float2 a = P.ay2[i][ph];
+#pragma unroll
+          for (int pw = 0; pw < kP; ++pw) acc[ph * kP + pw] = __ffma2_rn(a, rx[pw], acc[ph * kP + pw]);
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&f.empty[st]);       // this warp is done with stage st
       }
     }
   }
-  __syncthreads();
-  // pooled block -> shared [C][49] (lane stride 49 elements: conflict-free) -> one bulk store
-  const float inv = 1.f / r.count;          // count = sr*sr: a power of two
-  T* so = reinterpret_cast<T*>(ring) + tid * kNB;
+  __syncthreads();                          // every warp is done with the ring
+  // pooled block -> shared [C][49] -> one bulk store
+  if (tid < NC) {
+    T* so = reinterpret_cast<T*>(ring) + (2 * tid) * kNB;
 #pragma unroll
-  for (int i = 0; i < kNB; ++i) so[i] = from_f32<T>(acc[i] * inv);
+    for (int i = 0; i < kNB; ++i) {
+      so[i] = from_f32<T>(acc[i].x * inv);
+      so[kNB + i] = from_f32<T>(acc[i].y * inv);
+    }
+  }
   fence_proxy_async_smem();
   __syncthreads();
   if (tid == 0) {
-    bulk_store(out + (size_t)k * C * kNB, ring, (unsigned)(C * kNB * sizeof(T)));
+    bulk_store_hint(out + (size_t)k * C * kNB, ring, (unsigned)(C * kNB * sizeof(T)), policy_evict_first());
     bulk_commit();
     bulk_wait_read<0>();
   }
@@ -322,286 +459,284 @@ msroi_fwd_tma_kernel(const RoiDev g, const float* __restrict__ rois, int n_rois,
 // ================================================================================================
 // Backward
 // ================================================================================================
-// One RoI by one CTA (blockDim.x == C).  ring: gradient-block staging [C][49], then row buffers.
+struct alignas(16) BwdSync {
+  alignas(8) unsigned long long plan_full[kPlanBufBwd], plan_empty[kPlanBufBwd];
+  alignas(8) unsigned long long g_full, g_empty;
+};
+
+template <typename T, int C> struct BwdCfg {
+  static constexpr int kStaging = C * kNB * (int)sizeof(T);                       // gradient block of one RoI
+  static constexpr int kPlans = kPlanBufBwd * kPlanBwdBytes;
+  static constexpr int kRowBytesMax = kSpanMax * C * (int)sizeof(T);
+  static constexpr int kAvail = kSmemBudget - kStaging - kPlans - (int)sizeof(BwdSync) - 256;
+  static constexpr int kRing = 2 * kRowBytesMax;                                  // two fixed row buffers
+  static constexpr int kSmem = kStaging + kPlans + kRing;
+  static_assert(kRing <= (kAvail / 1024) * 1024, "shared-memory budget for 2 CTAs per SM");
+};
+
 template <typename T, int C, int SR>
-__device__ __forceinline__ void bwd_one_roi(const RoiDev& g, RoiSmem& t, unsigned char* ring, const T* __restrict__ grad_out,
-                                            const float* __restrict__ rois, int k, unsigned gbar_parity) {
+__global__ void __launch_bounds__(C / 2 + 32, 2)
+msroi_bwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, const T* __restrict__ grad_out, int n_rois,
+                     int* __restrict__ zero_done) {
   constexpr int NS = kP * SR;
+  constexpr int NC = C / 2;
   constexpr int PIX = C * (int)sizeof(T);
+  constexpr int RING = BwdCfg<T, C>::kRing;
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* staging = smem;                                          // [C][49] gradient block
+  unsigned char* plan_buf = smem + BwdCfg<T, C>::kStaging;
+  unsigned char* ring = plan_buf + BwdCfg<T, C>::kPlans;                  // row buffers
+  __shared__ BwdSync f;
   const int tid = threadIdx.x;
-  // caller guarantees: no bulk operation of this CTA still reads `ring`, and a __syncthreads() since
+  const int nj = (n_rois - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
   if (tid == 0) {
-    mbar_expect_tx(&t.gbar, (unsigned)(C * kNB * sizeof(T)));
-    bulk_load(ring, grad_out + (size_t)k * C * kNB, (unsigned)(C * kNB * sizeof(T)), &t.gbar);
-    t.geo = roi_geometry(g, rois + (size_t)k * 5);
+#pragma unroll
+    for (int i = 0; i < kPlanBufBwd; ++i) {
+      mbar_init(&f.plan_full[i], 1);
+      mbar_init(&f.plan_empty[i], NC / 32);
+    }
+    mbar_init(&f.g_full, 1);
+    mbar_init(&f.g_empty, NC / 32);
+    mbar_fence_init();
   }
   __syncthreads();
-  const RoiGeom r = t.geo;
-  const bool usable = r.batch >= 0 && r.batch < g.B;
-  if (usable) {
-    if (tid < 32) fill_axis_samples(t.ylo, t.yhi, t.yl, t.yh, tid, NS, SR, r.start_h, r.bin_h, r.H);
-    else if (tid < 64) fill_axis_samples(t.xlo, t.xhi, t.xl, t.xh, tid - 32, NS, SR, r.start_w, r.bin_w, r.W);
-  }
-  __syncthreads();
-  int n_rows = 0;
-  if (usable) {
-    build_lists<SR>(t, tid);
-    n_rows = (t.x_first <= t.x_last) ? t.n_rows : 0;
-  }
-  const int x_first = t.x_first, slot_mode = t.slot_mode;
-  const int row_px = n_rows ? (slot_mode ? 2 * t.n_slots : (t.x_last - x_first + 1)) : 1;
-  const unsigned row_bytes = (unsigned)row_px * PIX;
-  const int n_buf = min(4, kBwdRing / (int)row_bytes);        // 2..4 row buffers
-  if (n_rows) {
-    const float inv = 1.f / (float)(SR * SR);                 // the CPU backward divides by the raw grid product
-    for (int e = tid; e < kMaxLive * 8; e += C) {
-      const int i = e >> 3, p = e & 7;
-      t.ay[i][p] = (i < n_rows && p < kP) ? axis_weight(t.ylo, t.yhi, t.yl, t.yh, t.rows[i], p, SR) * inv : 0.f;
+
+  if (tid == NC) {
+    // ------------------------------------------------------------------ producer: plans and gradient blocks
+    const unsigned long long stream = policy_evict_first();
+    for (int j = 0; j < nj; ++j) {
+      const size_t k = (size_t)blockIdx.x + (size_t)j * gridDim.x;
+      const int s = j % kPlanBufBwd;
+      if (j >= kPlanBufBwd) mbar_wait(&f.plan_empty[s], (unsigned)(j / kPlanBufBwd - 1) & 1u);
+      mbar_expect_tx(&f.plan_full[s], kPlanBwdBytes);
+      bulk_load_hint(plan_buf + s * kPlanBwdBytes, plans + k, kPlanBwdBytes, &f.plan_full[s], stream);
+      if (j >= 1) mbar_wait(&f.g_empty, (unsigned)(j - 1) & 1u);    // consumers copied block j-1 to registers
+      mbar_expect_tx(&f.g_full, (unsigned)(C * kNB * sizeof(T)));
+      bulk_load_hint(staging, grad_out + k * C * kNB, (unsigned)(C * kNB * sizeof(T)), &f.g_full, stream);
     }
-    if (!slot_mode) {
-      for (int e = tid; e < kSpanMax * 8; e += C) {
-        const int i = e >> 3, p = e & 7;
-        t.ax[i][p] = (i < row_px && p < kP) ? axis_weight(t.xlo, t.xhi, t.xl, t.xh, x_first + i, p, SR) : 0.f;
+  } else if (tid < NC) {
+    // ------------------------------------------------------------------ consumers: channels 2*tid, 2*tid+1
+    int zeroed_upto = -1, cur_img = -1;
+    const unsigned long long keep = policy_evict_last();   // gradient maps of the images in flight stay in L2
+    auto zero_share = [&](int b) {       // this CTA's share of image b's gradient maps
+      for (int l = 0; l < g.n_levels; ++l) {
+        const size_t n16 = (size_t)g.H[l] * g.W[l] * C * sizeof(T) / 16;
+        uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<T*>(g.gfeat[l]) + (size_t)b * g.H[l] * g.W[l] * C);
+        for (size_t i = (size_t)blockIdx.x * NC + tid; i < n16; i += (size_t)gridDim.x * NC) st_zero16_hint(p + i, keep);
       }
-    }
-  }
-  // the gradient block has landed: 49 values of this thread's channel -> registers
-  mbar_wait(&t.gbar, gbar_parity);
-  float gr[kNB];
-  {
-    const T* sg = reinterpret_cast<const T*>(ring) + tid * kNB;
+      asm volatile("fence.proxy.async.global;\n" ::: "memory");   // generic-proxy zeros before the bulk engine's RMW
+      __threadfence();
+      consumer_barrier<NC>();
+      if (tid == 0) atomicAdd(&zero_done[b], 1);
+    };
+    unsigned issued = 0;                 // row reductions committed by thread 0 (ring position)
+    for (int j = 0; j < nj; ++j) {
+      const int s = j % kPlanBufBwd;
+      mbar_wait(&f.plan_full[s], (unsigned)(j / kPlanBufBwd) & 1u);
+      const RoiPlan& P = *reinterpret_cast<const RoiPlan*>(plan_buf + s * kPlanBwdBytes);
+      const int n_rows = P.n_rows;
+      // the gradient block: 49 values of this thread's two channels -> registers, pre-divided by count
+      mbar_wait(&f.g_full, (unsigned)j & 1u);
+      float2 gr[kNB];
+      {
+        const float inv = P.inv_count;
+        const T* sg = reinterpret_cast<const T*>(staging) + (2 * tid) * kNB;
 #pragma unroll
-    for (int i = 0; i < kNB; ++i) gr[i] = to_f32<T>(sg[i]);
-  }
-  __syncthreads();                          // staging consumed, tables visible
-  if (!n_rows) return;
-  T* __restrict__ img = reinterpret_cast<T*>(g.gfeat[r.level]) + (size_t)r.batch * r.H * r.W * C;
-  for (int i = 0; i < n_rows; ++i) {
-    const float4 a0 = *reinterpret_cast<const float4*>(&t.ay[i][0]);
-    const float4 a1 = *reinterpret_cast<const float4*>(&t.ay[i][4]);
-    float tq[kP];
-#pragma unroll
-    for (int pw = 0; pw < kP; ++pw) {
-      float s = a0.x * gr[0 * kP + pw];
-      s = fmaf(a0.y, gr[1 * kP + pw], s);
-      s = fmaf(a0.z, gr[2 * kP + pw], s);
-      s = fmaf(a0.w, gr[3 * kP + pw], s);
-      s = fmaf(a1.x, gr[4 * kP + pw], s);
-      s = fmaf(a1.y, gr[5 * kP + pw], s);
-      s = fmaf(a1.z, gr[6 * kP + pw], s);
-      tq[pw] = s;
-    }
-    unsigned char* buf = ring + (size_t)(i % n_buf) * row_bytes;
-    T* __restrict__ row = reinterpret_cast<T*>(buf) + tid;
-    if (!slot_mode) {
-#pragma unroll 4
-      for (int x = 0; x < row_px; ++x) {
-        const float4 w0 = *reinterpret_cast<const float4*>(&t.ax[x][0]);
-        const float4 w1 = *reinterpret_cast<const float4*>(&t.ax[x][4]);
-        float v = w0.x * tq[0];
-        v = fmaf(w0.y, tq[1], v); v = fmaf(w0.z, tq[2], v); v = fmaf(w0.w, tq[3], v);
-        v = fmaf(w1.x, tq[4], v); v = fmaf(w1.y, tq[5], v); v = fmaf(w1.z, tq[6], v);
-        row[x * C] = from_f32<T>(v);
+        for (int i = 0; i < kNB; ++i) gr[i] = make_float2(to_f32<T>(sg[i]) * inv, to_f32<T>(sg[kNB + i]) * inv);
       }
-    } else {
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&f.g_empty);
+      if (n_rows) {
+        const int b = P.batch;
+        while (zeroed_upto < min(b + 1, g.B - 1)) zero_share(++zeroed_upto);
+        if (b != cur_img) {
+          cur_img = b;
+          if (tid == 0) {
+            while (atomicAdd(&zero_done[b], 0) < (int)gridDim.x) __nanosleep(100);
+            __threadfence();
+          }
+          consumer_barrier<NC>();
+        }
+        const int slot_mode = P.slot_mode, row_px = P.row_px, W = g.W[P.level];
+        const unsigned row_bytes = (unsigned)row_px * PIX;
+        T* __restrict__ img = reinterpret_cast<T*>(g.gfeat[P.level]) + (size_t)b * g.H[P.level] * W * C;
+        for (int i = 0; i < n_rows; ++i) {
+          float2 tq[kP];
 #pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        const int slot = t.slot_of[s];
-        if (slot >= 0) {                    // warp-uniform
-          const bool two = t.xhi[s] != t.xlo[s];
-          row[(slot * 2) * C] = from_f32<T>((two ? t.xh[s] : t.xh[s] + t.xl[s]) * tq[s / SR]);
-          if (two) row[(slot * 2 + 1) * C] = from_f32<T>(t.xl[s] * tq[s / SR]);
+          for (int pw = 0; pw < kP; ++pw) tq[pw] = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int ph = 0; ph < kP; ++ph) {
+            const float2 a = P.ay2[i][ph];
+#pragma unroll
+            for (int pw = 0; pw < kP; ++pw) tq[pw] = __ffma2_rn(a, gr[ph * kP + pw], tq[pw]);
+          }
+          unsigned char* buf = ring + (size_t)(issued & 1u) * (RING / 2);     // two fixed buffers of the widest row
+          unsigned char* __restrict__ row = buf + tid * 2 * (int)sizeof(T);
+          if (!slot_mode) {
+#pragma unroll 2
+            for (int x = 0; x < row_px; ++x) {
+              const float4 w0 = *reinterpret_cast<const float4*>(&P.ax[x][0]);
+              const float4 w1 = *reinterpret_cast<const float4*>(&P.ax[x][4]);
+              float2 v = __fmul2_rn(make_float2(w0.x, w0.x), tq[0]);
+              v = __ffma2_rn(make_float2(w0.y, w0.y), tq[1], v);
+              v = __ffma2_rn(make_float2(w0.z, w0.z), tq[2], v);
+              v = __ffma2_rn(make_float2(w0.w, w0.w), tq[3], v);
+              v = __ffma2_rn(make_float2(w1.x, w1.x), tq[4], v);
+              v = __ffma2_rn(make_float2(w1.y, w1.y), tq[5], v);
+              v = __ffma2_rn(make_float2(w1.z, w1.z), tq[6], v);
+              st_pair<T>(row + x * PIX, v);
+            }
+          } else {
+#pragma unroll
+            for (int sx = 0; sx < NS; ++sx) {
+              const int slot = P.slot_of[sx];
+              if (slot >= 0) {                  // warp-uniform
+                const float h = P.xs[sx].hx, l = P.xs[sx].lx;
+                const bool two = P.slot_two[sx];
+                const float w0 = two ? h : h + l;
+                st_pair<T>(row + (slot * 2) * PIX, __fmul2_rn(make_float2(w0, w0), tq[sx / SR]));
+                if (two) st_pair<T>(row + (slot * 2 + 1) * PIX, __fmul2_rn(make_float2(l, l), tq[sx / SR]));
+              }
+            }
+          }
+          fence_proxy_async_smem();             // generic-proxy writes -> visible to the bulk engine
+          if (tid == 0) bulk_wait_read<0>();    // the buffer the NEXT row will write has been read
+          consumer_barrier<NC>();
+          if (tid == 0) {
+            const size_t yw = (size_t)P.rows[i] * W;
+            if (!slot_mode) {
+              bulk_reduce_add_hint<T>(img + (yw + P.x_first) * C, buf, row_bytes, keep);
+            } else {
+              for (int sx = 0; sx < NS; ++sx)
+                if (P.slot_of[sx] >= 0)
+                  bulk_reduce_add_hint<T>(img + (yw + P.slot_x[sx]) * C, buf + (size_t)P.slot_of[sx] * 2 * PIX,
+                                          P.slot_two[sx] ? 2u * PIX : (unsigned)PIX, keep);
+            }
+            bulk_commit();
+          }
+          ++issued;
         }
       }
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&f.plan_empty[s]);
     }
-    fence_proxy_async_smem();               // generic-proxy writes -> visible to the bulk engine
-    if (tid == 0) {                         // the buffer the NEXT row will write must have been read
-      if (n_buf == 2) bulk_wait_read<0>();
-      else if (n_buf == 3) bulk_wait_read<1>();
-      else bulk_wait_read<2>();
-    }
-    __syncthreads();
-    if (tid == 0) {
-      const size_t y = (size_t)t.rows[i];
-      if (!slot_mode) {
-        bulk_reduce_add<T>(img + (y * r.W + x_first) * C, buf, row_bytes);
-      } else {
-        for (int s = 0; s < NS; ++s)
-          if (t.slot_of[s] >= 0)
-            bulk_reduce_add<T>(img + (y * r.W + t.xlo[s]) * C, buf + (size_t)t.slot_of[s] * 2 * PIX,
-                               (t.xhi[s] != t.xlo[s]) ? 2u * PIX : (unsigned)PIX);
-      }
-      bulk_commit();
-    }
+    while (zeroed_upto < g.B - 1) zero_share(++zeroed_upto);   // images this CTA never reached
+    if (tid == 0) bulk_wait_read<0>();
   }
-}
-
-// One CTA per RoI; gradients must have been zero-filled.
-template <typename T, int C, int SR>
-__global__ void __launch_bounds__(C, (C == 256) ? 3 : 4)
-msroi_bwd_tma_kernel(const RoiDev g, const T* __restrict__ grad_out, const float* __restrict__ rois, int n_rois) {
-  extern __shared__ __align__(128) unsigned char ring[];
-  __shared__ RoiSmem t;
-  if (threadIdx.x == 0) {
-    mbar_init(&t.gbar, 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  bwd_one_roi<T, C, SR>(g, t, ring, grad_out, rois, blockIdx.x, 0u);
-  if (threadIdx.x == 0) bulk_wait_read<0>();
-}
-
-// Persistent cooperative variant.  Every CTA zero-fills its share of image b+1's gradient maps
-// BEFORE it starts on image b's RoIs and publishes that in zero_done[b+1]; an RoI of image b is
-// only started once zero_done[b] == gridDim.x.  All CTAs are co-resident (cooperative launch), so
-// the wait cannot deadlock, and in steady state nobody waits: the zero-filled lines of an image
-// (52.9 MB fp32 at 608x1024) are still dirty in L2 when the reductions arrive.
-template <typename T, int C, int SR>
-__global__ void __launch_bounds__(C, (C == 256) ? 3 : 4)
-msroi_bwd_tma_persistent_kernel(const RoiDev g, const T* __restrict__ grad_out, const float* __restrict__ rois,
-                                const int32_t* __restrict__ roi_img_offsets, int* __restrict__ counters) {
-  extern __shared__ __align__(128) unsigned char ring[];
-  __shared__ RoiSmem t;
-  int* work = counters;                 // [B] next RoI of image b
-  int* zero_done = counters + g.B;      // [B] CTAs that finished zero-filling image b
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    mbar_init(&t.gbar, 1);
-    mbar_fence_init();
-  }
-  auto zero_image = [&](int b) {
-    for (int l = 0; l < g.n_levels; ++l) {
-      const size_t n16 = (size_t)g.H[l] * g.W[l] * C * sizeof(T) / 16;
-      uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<T*>(g.gfeat[l]) + (size_t)b * g.H[l] * g.W[l] * C);
-      for (size_t i = (size_t)blockIdx.x * C + tid; i < n16; i += (size_t)gridDim.x * C) p[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    asm volatile("fence.proxy.async.global;\n" ::: "memory");   // generic-proxy zeros before the bulk engine's RMW
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) atomicAdd(&zero_done[b], 1);
-  };
-  zero_image(0);
-  unsigned n_done = 0;                  // RoIs processed by this CTA (parity of the staging barrier)
-  for (int b = 0; b < g.B; ++b) {
-    if (b + 1 < g.B) zero_image(b + 1);
-    if (tid == 0) {
-      while (atomicAdd(&zero_done[b], 0) < (int)gridDim.x) __nanosleep(200);
-      __threadfence();
-    }
-    const int k0 = roi_img_offsets[b], k1 = roi_img_offsets[b + 1];
-    while (true) {
-      if (tid == 0) {
-        bulk_wait_read<0>();            // row buffers of the previous RoI have been read
-        t.next_k = k0 + atomicAdd(&work[b], 1);
-      }
-      __syncthreads();
-      const int k = t.next_k;
-      if (k >= k1) break;
-      bwd_one_roi<T, C, SR>(g, t, ring, grad_out, rois, k, n_done & 1u);
-      ++n_done;
-    }
-    __syncthreads();
-  }
-  if (tid == 0) bulk_wait_read<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
-static bool tma_shape_ok(const dgod_roi_config* cfg, const RoiDev& g) {
+static bool tma_shape_ok(const RoiDev& g) {
   if (!g.channels_last || g.PH != kP || g.PW != kP) return false;
   if (g.sr < 1 || g.sr > 2) return false;
   if (!(g.C == 256 || ((g.C == 128 || g.C == 64) && g.sr == 2))) return false;   // instantiated shapes
+  if (g.B > kCounterBytes / (int)sizeof(int)) return false;
   for (int l = 0; l < g.n_levels; ++l)
     if (g.H[l] > 32000 || g.W[l] > 32000) return false;
-  (void)cfg;
   return true;
 }
 
+size_t msroi_tma_workspace(int n_rois) {
+  return (size_t)kCounterBytes + (size_t)(n_rois > 0 ? n_rois : 1) * sizeof(RoiPlan);
+}
+
+static int launch_plan(const RoiDev& g, const float* rois, int n_rois, RoiPlan* plans, int pix_bytes, int want_ax, cudaStream_t st) {
+  msroi_plan_kernel<<<cdiv(n_rois, kPlanWarps), kPlanWarps * 32, 0, st>>>(g, rois, n_rois, plans, pix_bytes, want_ax);
+  DGOD_LAUNCHED();
+  return DGOD_OK;
+}
+
 template <typename T, int C, int SR>
-static int launch_fwd_tma(const RoiDev& g, const float* rois, int n_rois, void* out, cudaStream_t st) {
+static int launch_fwd_tma(const RoiDev& g, const float* rois, int n_rois, void* out, RoiPlan* plans, cudaStream_t st) {
+  constexpr int kSmem = FwdCfg<T, C>::kSmem;
   static bool attr = false;
   if (!attr) {
-    DGOD_CUDA(cudaFuncSetAttribute(msroi_fwd_tma_kernel<T, C, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdRing));
+    DGOD_CUDA(cudaFuncSetAttribute(msroi_fwd_tma_kernel<T, C, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr = true;
   }
-  msroi_fwd_tma_kernel<T, C, SR><<<n_rois, C, kFwdRing, st>>>(g, rois, n_rois, (T*)out);
+  int rc = launch_plan(g, rois, n_rois, plans, C * (int)sizeof(T), 0, st);
+  if (rc) return rc;
+  msroi_fwd_tma_kernel<T, C, SR><<<n_rois, C / 2 + 32, kSmem, st>>>(g, plans, n_rois, (T*)out);
   DGOD_LAUNCHED();
   return DGOD_OK;
 }
 
 template <typename T>
-static int dispatch_fwd_tma(const RoiDev& g, const float* rois, int n_rois, void* out, cudaStream_t st) {
-  if (g.C == 256) return g.sr == 2 ? launch_fwd_tma<T, 256, 2>(g, rois, n_rois, out, st) : launch_fwd_tma<T, 256, 1>(g, rois, n_rois, out, st);
-  if (g.C == 128) return launch_fwd_tma<T, 128, 2>(g, rois, n_rois, out, st);
-  return launch_fwd_tma<T, 64, 2>(g, rois, n_rois, out, st);
+static int dispatch_fwd_tma(const RoiDev& g, const float* rois, int n_rois, void* out, RoiPlan* plans, cudaStream_t st) {
+  if (g.C == 256)
+    return g.sr == 2 ? launch_fwd_tma<T, 256, 2>(g, rois, n_rois, out, plans, st) : launch_fwd_tma<T, 256, 1>(g, rois, n_rois, out, plans, st);
+  if (g.C == 128) return launch_fwd_tma<T, 128, 2>(g, rois, n_rois, out, plans, st);
+  return launch_fwd_tma<T, 64, 2>(g, rois, n_rois, out, plans, st);
 }
 
-int msroi_fwd_tma(const dgod_roi_config* cfg, const RoiDev& g, const float* rois, int n_rois, void* out,
-                  cudaStream_t st, int* handled) {
+int msroi_fwd_tma(const dgod_roi_config* cfg, const RoiDev& g, const float* rois, int n_rois, void* out, void* workspace,
+                  size_t workspace_bytes, cudaStream_t st, int* handled) {
   *handled = 0;
-  if (!tma_shape_ok(cfg, g) || ((uintptr_t)out & 15)) return DGOD_OK;
+  if (!tma_shape_ok(g) || ((uintptr_t)out & 15)) return DGOD_OK;
+  if (!workspace || workspace_bytes < msroi_tma_workspace(n_rois) || ((uintptr_t)workspace & 127)) return DGOD_OK;
   for (int l = 0; l < g.n_levels; ++l)
     if ((uintptr_t)g.feat[l] & 15) return DGOD_OK;
   *handled = 1;
-  return cfg->dtype == DGOD_F32 ? dispatch_fwd_tma<float>(g, rois, n_rois, out, st)
-                                : dispatch_fwd_tma<__nv_bfloat16>(g, rois, n_rois, out, st);
+  RoiPlan* plans = reinterpret_cast<RoiPlan*>((char*)workspace + kCounterBytes);
+  return cfg->dtype == DGOD_F32 ? dispatch_fwd_tma<float>(g, rois, n_rois, out, plans, st)
+                                : dispatch_fwd_tma<__nv_bfloat16>(g, rois, n_rois, out, plans, st);
 }
 
 template <typename T, int C, int SR>
-static int launch_bwd_tma(const RoiDev& g, const void* grad_out, const float* rois, int n_rois,
-                          const int32_t* roi_img_offsets, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  static bool attr = false;
-  static int coop = 0, n_sm = 0, per_sm = 0;
-  if (!attr) {
-    int dev = 0;
+static int launch_bwd_tma(const RoiDev& g, const void* grad_out, const float* rois, int n_rois, void* workspace,
+                          cudaStream_t st, int* handled) {
+  constexpr int kSmem = BwdCfg<T, C>::kSmem;
+  static bool init = false;
+  static int coop = 0, n_cta = 0;
+  if (!init) {
+    int dev = 0, n_sm = 0, per_sm = 0;
     DGOD_CUDA(cudaGetDevice(&dev));
     DGOD_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     DGOD_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    DGOD_CUDA(cudaFuncSetAttribute(msroi_bwd_tma_kernel<T, C, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdRing));
-    DGOD_CUDA(cudaFuncSetAttribute(msroi_bwd_tma_persistent_kernel<T, C, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdRing));
-    DGOD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msroi_bwd_tma_persistent_kernel<T, C, SR>, C, kBwdRing));
-    attr = true;
+    DGOD_CUDA(cudaFuncSetAttribute(msroi_bwd_tma_kernel<T, C, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    DGOD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msroi_bwd_tma_kernel<T, C, SR>, C / 2 + 32, kSmem));
+    n_cta = n_sm * per_sm;
+    init = true;
   }
-  const size_t need_ws = 2 * (size_t)g.B * sizeof(int);
-  if (coop && per_sm >= 1 && roi_img_offsets && workspace && workspace_bytes >= need_ws) {
-    int* counters = (int*)workspace;
-    DGOD_CUDA(cudaMemsetAsync(counters, 0, need_ws, st));
-    const T* go = (const T*)grad_out;
-    RoiDev gg = g;
-    void* args[] = {(void*)&gg, (void*)&go, (void*)&rois, (void*)&roi_img_offsets, (void*)&counters};
-    DGOD_CUDA(cudaLaunchCooperativeKernel((const void*)msroi_bwd_tma_persistent_kernel<T, C, SR>, dim3(per_sm * n_sm), dim3(C), args,
-                                          kBwdRing, st));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return DGOD_OK;
+  if (!coop || n_cta < 1) return DGOD_OK;                 // not handled: the caller falls back
+  *handled = 1;
+  int* zero_done = (int*)workspace;
+  RoiPlan* plans = reinterpret_cast<RoiPlan*>((char*)workspace + kCounterBytes);
+  DGOD_CUDA(cudaMemsetAsync(zero_done, 0, (size_t)g.B * sizeof(int), st));
+  if (n_rois > 0) {
+    int rc = launch_plan(g, rois, n_rois, plans, C * (int)sizeof(T), 1, st);
+    if (rc) return rc;
   }
-  for (int l = 0; l < g.n_levels; ++l)
-    DGOD_CUDA(cudaMemsetAsync(g.gfeat[l], 0, (size_t)g.B * g.C * g.H[l] * g.W[l] * sizeof(T), st));
-  if (n_rois == 0) return DGOD_OK;
-  msroi_bwd_tma_kernel<T, C, SR><<<n_rois, C, kBwdRing, st>>>(g, (const T*)grad_out, rois, n_rois);
-  DGOD_LAUNCHED();
+  // every CTA takes part in the zero fill (all of them are co-resident: cooperative launch)
+  const T* go = (const T*)grad_out;
+  const RoiPlan* cplans = plans;
+  RoiDev gg = g;
+  void* args[] = {(void*)&gg, (void*)&cplans, (void*)&go, (void*)&n_rois, (void*)&zero_done};
+  DGOD_CUDA(cudaLaunchCooperativeKernel((const void*)msroi_bwd_tma_kernel<T, C, SR>, dim3(n_cta), dim3(C / 2 + 32), args, kSmem, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return DGOD_OK;
 }
 
 template <typename T>
-static int dispatch_bwd_tma(const RoiDev& g, const void* grad_out, const float* rois, int n_rois, const int32_t* offs,
-                            void* ws, size_t wsb, cudaStream_t st) {
+static int dispatch_bwd_tma(const RoiDev& g, const void* grad_out, const float* rois, int n_rois, void* ws, cudaStream_t st,
+                            int* handled) {
   if (g.C == 256)
-    return g.sr == 2 ? launch_bwd_tma<T, 256, 2>(g, grad_out, rois, n_rois, offs, ws, wsb, st)
-                     : launch_bwd_tma<T, 256, 1>(g, grad_out, rois, n_rois, offs, ws, wsb, st);
-  if (g.C == 128) return launch_bwd_tma<T, 128, 2>(g, grad_out, rois, n_rois, offs, ws, wsb, st);
-  return launch_bwd_tma<T, 64, 2>(g, grad_out, rois, n_rois, offs, ws, wsb, st);
+    return g.sr == 2 ? launch_bwd_tma<T, 256, 2>(g, grad_out, rois, n_rois, ws, st, handled)
+                     : launch_bwd_tma<T, 256, 1>(g, grad_out, rois, n_rois, ws, st, handled);
+  if (g.C == 128) return launch_bwd_tma<T, 128, 2>(g, grad_out, rois, n_rois, ws, st, handled);
+  return launch_bwd_tma<T, 64, 2>(g, grad_out, rois, n_rois, ws, st, handled);
 }
 
 int msroi_bwd_tma(const dgod_roi_config* cfg, const RoiDev& g, const void* grad_out, const float* rois, int n_rois,
-                  const int32_t* roi_img_offsets, void* workspace, size_t workspace_bytes, cudaStream_t st,
-                  int* handled) {
+                  void* workspace, size_t workspace_bytes, cudaStream_t st, int* handled) {
   *handled = 0;
-  if (!tma_shape_ok(cfg, g) || ((uintptr_t)grad_out & 15)) return DGOD_OK;
+  if (!tma_shape_ok(g) || ((uintptr_t)grad_out & 15)) return DGOD_OK;
+  if (!workspace || workspace_bytes < msroi_tma_workspace(n_rois) || ((uintptr_t)workspace & 127)) return DGOD_OK;
   for (int l = 0; l < g.n_levels; ++l)
     if ((uintptr_t)g.gfeat[l] & 15) return DGOD_OK;
-  *handled = 1;
-  return cfg->dtype == DGOD_F32
-             ? dispatch_bwd_tma<float>(g, grad_out, rois, n_rois, roi_img_offsets, workspace, workspace_bytes, st)
-             : dispatch_bwd_tma<__nv_bfloat16>(g, grad_out, rois, n_rois, roi_img_offsets, workspace, workspace_bytes, st);
+  return cfg->dtype == DGOD_F32 ? dispatch_bwd_tma<float>(g, grad_out, rois, n_rois, workspace, st, handled)
+                                : dispatch_bwd_tma<__nv_bfloat16>(g, grad_out, rois, n_rois, workspace, st, handled);
 }
 
 }  // namespace dgod

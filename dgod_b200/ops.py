@@ -414,7 +414,9 @@ def _msroi_fwd_op(feats: List[Tensor], rois: Tensor, roi_img_offsets: Optional[T
     ptrs, keep_alive = _level_ptrs(fs)
     tok = KernelTimer.start("msroi_align_fwd", _roi_bytes([f.numel() for f in fs], f0.element_size(), n,
                                                           f0.shape[1], pooled_h, pooled_w, sampling_ratio))
-    check(lib.dgod_msroi_align_fwd(C.byref(cfg), ptrs, _p(rois), n, _p(out), _stream()))
+    wsb = lib.dgod_msroi_align_fwd_workspace_bytes(n)
+    ws = _ws(wsb, f0.device)
+    check(lib.dgod_msroi_align_fwd(C.byref(cfg), ptrs, _p(rois), n, _p(out), _p(ws), wsb, _stream()))
     KernelTimer.stop(tok)
     return out
 

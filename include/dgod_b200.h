@@ -189,15 +189,20 @@ typedef struct {
 /* rois: device [K,5] fp32 (batch index, x1, y1, x2, y2) in image coordinates (TV
  * ops/poolers.py:87-95).  roi_img_offsets (optional, device [batch+1]) promises that rois are
  * grouped by image; the backward uses it to bound its per-tile scan.  out: [K,C,PH,PW]. */
+size_t dgod_msroi_align_fwd_workspace_bytes(int n_rois);
+/* workspace (optional, 128-byte aligned, dgod_msroi_align_fwd_workspace_bytes(n_rois) bytes) holds the
+ * per-RoI plans of the TMA kernel (channels_last, 7x7 bins, sampling_ratio 1..2, C in {64,128,256});
+ * without it, or for other shapes, the table-driven / generic kernels run. */
 int dgod_msroi_align_fwd(const dgod_roi_config* cfg /*host*/,
                          const void* const* feats /*host array of device ptrs*/,
-                         const float* rois, int n_rois, void* out, dgod_stream_t stream);
+                         const float* rois, int n_rois, void* out,
+                         void* workspace, size_t workspace_bytes, dgod_stream_t stream);
 size_t dgod_msroi_align_bwd_workspace_bytes(int n_rois);
 /* grad_feats[l] is fully overwritten (zero where no RoI contributes): no memset required.
  * algo 0 picks the TMA bulk-reduce kernel when the shape allows (channels_last, 7x7 bins,
- * sampling_ratio 1..2, 64 <= C <= 256, C % 32 == 0), else the vector-RED / atomic scatter (fp32) or
+ * sampling_ratio 1..2, C in {64,128,256}, cooperative launch), else the vector-RED / atomic scatter (fp32) or
  * the deterministic tile gather (bf16); 1 forces the scatter, 2 the tile gather, 3 the TMA kernel.
- * workspace: dgod_msroi_align_bwd_workspace_bytes(n_rois) bytes (RoI records / work counters). */
+ * workspace: dgod_msroi_align_bwd_workspace_bytes(n_rois) bytes, 128-byte aligned (RoI plans, counters). */
 int dgod_msroi_align_bwd(const dgod_roi_config* cfg /*host*/,
                          const void* grad_out /*device [K,C,PH,PW]*/,
                          const float* rois, int n_rois,
