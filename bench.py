@@ -267,8 +267,15 @@ def run_b200(args):
         top = max((k for k in kern if k.startswith("msroi")), key=lambda k: kern[k][1], default=max(kern, key=lambda k: kern[k][1]))
         n, tot_ms, tot_bytes = kern[top]
         ach = tot_bytes / 1e9 / (tot_ms / 1e3)
+        traffic = None
+        tf = ROOT / "profiles" / "roofline_traffic.json"
+        if tf.exists():
+            try:
+                traffic = json.loads(tf.read_text()).get(top)
+            except Exception:
+                traffic = None
         roof = {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "launches": n, "avg_launch_us": round(1e3 * tot_ms / n, 2)}
     out = {
         "metric": "DGFRCNN dg train img/s", "value": round(value, 3), "unit": "img/s", "n_gpus": world,

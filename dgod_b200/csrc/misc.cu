@@ -127,9 +127,52 @@ detect_candidates_kernel(const float* __restrict__ logits, const float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------- NCHW -> NHWC
+// [B][C][HW] -> [B][HW][C] through a 64x64 shared-memory tile (+1 padding: conflict-free both
+// ways).  Reads are contiguous along HW, writes contiguous along C: pure HBM traffic, 2*n*s bytes.
+// Lets NCHW feature maps (torchvision's default layout) take the channels_last TMA RoIAlign path.
+template <typename T>
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int C, int HW) {
+  __shared__ T tile[64][65];
+  const int b = blockIdx.z;
+  const int hw0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const T* __restrict__ s = src + (size_t)b * C * HW;
+  T* __restrict__ d = dst + (size_t)b * C * HW;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;       // 64 x 4
+#pragma unroll 4
+  for (int i = ty; i < 64; i += 4) {
+    const int c = c0 + i, hw = hw0 + tx;
+    if (c < C && hw < HW) tile[i][tx] = s[(size_t)c * HW + hw];
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int i = ty; i < 64; i += 4) {
+    const int hw = hw0 + i, c = c0 + tx;
+    if (c < C && hw < HW) d[(size_t)hw * C + c] = tile[tx][i];
+  }
+}
+
 }  // namespace dgod
 
 using namespace dgod;
+
+extern "C" int dgod_nchw_to_nhwc(const void* src, void* dst, int batch, int channels, int hw, int dtype,
+                                 dgod_stream_t stream) {
+  DGOD_REQUIRE(batch >= 0 && channels >= 0 && hw >= 0, "dgod_nchw_to_nhwc: negative size");
+  DGOD_REQUIRE(dtype == DGOD_F32 || dtype == DGOD_BF16, "dgod_nchw_to_nhwc: unsupported dtype");
+  if (batch == 0 || channels == 0 || hw == 0) return DGOD_OK;
+  DGOD_REQUIRE(src && dst, "dgod_nchw_to_nhwc: null pointer");
+  DGOD_REQUIRE(batch <= 65535 && cdiv(channels, 64) <= 65535, "dgod_nchw_to_nhwc: grid too large");
+  dim3 grid(cdiv(hw, 64), cdiv(channels, 64), batch);
+  if (dtype == DGOD_F32)
+    nchw_to_nhwc_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, (float*)dst, channels, hw);
+  else
+    nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst,
+                                                                           channels, hw);
+  DGOD_LAUNCHED();
+  return DGOD_OK;
+}
 
 extern "C" int dgod_grl_scale(const void* grad, void* out, int64_t n, float alpha, int dtype,
                               dgod_stream_t stream) {

@@ -628,7 +628,7 @@ msroi_bwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, const T*
 
 // ------------------------------------------------------------------------------------------------
 static bool tma_shape_ok(const RoiDev& g) {
-  if (!g.channels_last || g.PH != kP || g.PW != kP) return false;
+  if (!g.channels_last || g.aligned || g.PH != kP || g.PW != kP) return false;   // DGOD: aligned=False (fasterrcnn.py:412-416)
   if (g.sr < 1 || g.sr > 2) return false;
   if (!(g.C == 256 || ((g.C == 128 || g.C == 64) && g.sr == 2))) return false;   // instantiated shapes
   if (g.B > kCounterBytes / (int)sizeof(int)) return false;

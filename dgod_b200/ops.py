@@ -394,6 +394,25 @@ def _roi_bytes(feats_numel: Sequence[int], esz: int, n_rois: int, c: int, ph: in
     return n_rois * c * ph * pw * esz + 20 * n_rois + min(sum(feats_numel) * esz, n_rois * c * ph * g * pw * g * 4 * esz)
 
 
+def _tma_shape(c: int, ph: int, pw: int, sr: int) -> bool:
+    """Shapes the TMA RoIAlign kernels are instantiated for (csrc/roi_align_tma.cu)."""
+    return ph == 7 and pw == 7 and (c == 256 and sr in (1, 2) or c in (64, 128) and sr == 2)
+
+
+def to_channels_last(x: Tensor) -> Tensor:
+    """NCHW-contiguous [B,C,H,W] -> the same tensor in channels_last memory (dgod_nchw_to_nhwc)."""
+    _need_cuda(x)
+    if x.dim() != 4 or not x.is_contiguous() or x.dtype not in (torch.float32, torch.bfloat16):
+        return x.contiguous(memory_format=torch.channels_last)
+    out = torch.empty_like(x, memory_format=torch.channels_last)
+    b, c, h, w = x.shape
+    tok = KernelTimer.start("nchw_to_nhwc", 2 * x.numel() * x.element_size())
+    check(_lib.load().dgod_nchw_to_nhwc(_p(x), _p(out), b, c, h * w, _lib.F32 if x.dtype == torch.float32 else _lib.BF16,
+                                        _stream()))
+    KernelTimer.stop(tok)
+    return out
+
+
 @torch.library.custom_op("dgod_b200::msroi_align", mutates_args=())
 def _msroi_fwd_op(feats: List[Tensor], rois: Tensor, roi_img_offsets: Optional[Tensor], scales: List[float],
                   pooled_h: int, pooled_w: int, sampling_ratio: int, aligned: bool, k_min: int, k_max: int,
@@ -401,6 +420,12 @@ def _msroi_fwd_op(feats: List[Tensor], rois: Tensor, roi_img_offsets: Optional[T
     _need_cuda(rois, *feats)
     lib = _lib.load()
     f0 = feats[0]
+    if (f0.dim() == 4 and f0.is_contiguous() and f0.shape[2] * f0.shape[3] > 1 and not aligned and rois.shape[0] > 0
+            and _tma_shape(f0.shape[1], pooled_h, pooled_w, sampling_ratio)):
+        # NCHW maps: one transposing pass, then the channels_last TMA kernel (faster than the generic
+        # NCHW kernel even with the extra pass)
+        feats = [to_channels_last(f) if f.is_contiguous() else f for f in feats]
+        f0 = feats[0]
     cfg, nhwc = _roi_config(feats, scales, pooled_h, pooled_w, sampling_ratio, aligned, k_min, k_max,
                             canonical_scale, canonical_level)
     fs = [f if (f.is_contiguous(memory_format=torch.channels_last) if nhwc else f.is_contiguous())
@@ -436,6 +461,8 @@ def _msroi_bwd_op(grad: Tensor, rois: Tensor, roi_img_offsets: Optional[Tensor],
     lib = _lib.load()
     n_levels = len(scales)
     b, c = shapes[0], shapes[1]
+    if not channels_last and not aligned and algo in (0, 3) and _tma_shape(c, pooled_h, pooled_w, sampling_ratio):
+        channels_last = True     # gradients of NCHW maps are returned in channels_last memory (same values)
     mf = torch.channels_last if channels_last else torch.contiguous_format
     grads = [torch.empty((b, c, shapes[2 + 2 * l], shapes[3 + 2 * l]), dtype=grad.dtype, device=grad.device,
                          memory_format=mf) for l in range(n_levels)]

@@ -25,6 +25,7 @@
  *   dgod_box_decode         TV _utils.py:162-224 (TV roi_heads.py:692, fasterrcnn.py:294)
  *   dgod_detect_candidates  TV roi_heads.py:692-724 (softmax, clip, score/size filters)
  *   dgod_grl_scale          DGcommon.py:33-45 (GRLayer.backward)
+ *   dgod_nchw_to_nhwc       layout helper (no reference counterpart: torch's .contiguous(channels_last))
  */
 #ifndef DGOD_B200_H_
 #define DGOD_B200_H_
@@ -233,6 +234,14 @@ int dgod_detect_candidates(const float* class_logits /*[n_rows,n_cls]*/,
                            float score_thresh, float min_size,
                            float* cand_boxes, float* cand_scores, int64_t* cand_labels,
                            uint8_t* cand_valid, dgod_stream_t stream);
+
+/* ------------------------------------------------------------------ layout */
+
+/* [batch][channels][hw] -> [batch][hw][channels] (NCHW -> NHWC), fp32 or bf16.  Used by the host
+ * layer to give NCHW feature maps (torchvision's default layout, fasterrcnn.py:317) the
+ * channels_last RoIAlign kernels. */
+int dgod_nchw_to_nhwc(const void* src, void* dst, int batch, int channels, int hw, int dtype,
+                      dgod_stream_t stream);
 
 /* ------------------------------------------------------------------ gradient reversal */
 
