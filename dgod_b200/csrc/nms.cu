@@ -23,6 +23,7 @@
 // fp32 instructions each) are the real cost for large runs — see DESIGN.md for the roofline.
 #include "nms_core.cuh"
 #include "sort.cuh"
+#include <utility>
 
 namespace dgod {
 
@@ -313,10 +314,12 @@ nms_prepare_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
                    const int32_t* __restrict__ seg_offsets, int n_seg, int n_total, int n_pow2,
                    int offset_mode, unsigned long long* __restrict__ keys,
                    uint32_t* __restrict__ vals, uint32_t* __restrict__ seg_max,
+                   int32_t* __restrict__ seg_live /* optional: live records per segment */,
                    int32_t* __restrict__ status) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_pow2) return;
+  if (p >= n_pow2) return;     // n_pow2 is a multiple of the warp size or a single partial warp exits together
   unsigned long long key = kKeyMax;
+  int live_seg = -1;
   if (p < n_total && (!valid || valid[p])) {
     const int seg = find_segment(seg_offsets, n_seg, p);
     long long g = groups ? groups[p] : 0;
@@ -329,6 +332,11 @@ nms_prepare_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
     }
     key = ((unsigned long long)seg << 48) | ((unsigned long long)g << 32) |
           (unsigned long long)(~float_ordered(scores[p] + 0.f));  // -0 sorts like +0
+    live_seg = seg;
+  }
+  if (seg_live) {   // warp-aggregated count of the live records per segment
+    const unsigned peers = __match_any_sync(__activemask(), live_seg);
+    if (live_seg >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&seg_live[live_seg], __popc(peers));
   }
   keys[p] = key;
   vals[p] = (uint32_t)p;
@@ -359,12 +367,18 @@ nms_gather_kernel(const float* __restrict__ boxes, const int64_t* __restrict__ g
 
 __global__ void __launch_bounds__(256)
 nms_rekey_kernel(unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ keepbits,
-                 int n_pow2) {
+                 int n_pow2, int32_t* __restrict__ seg_live /* optional: kept records per segment */) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_pow2) return;
   const bool kept = (keepbits[p >> 6] >> (p & 63)) & 1ull;
   const unsigned long long key = keys[p];
-  keys[p] = (kept && key != kKeyMax) ? (key & ~(0xffffull << 32)) : kKeyMax;
+  const bool live = kept && key != kKeyMax;
+  keys[p] = live ? (key & ~(0xffffull << 32)) : kKeyMax;
+  if (seg_live) {
+    const int live_seg = live ? (int)(key >> 48) : -1;
+    const unsigned peers = __match_any_sync(__activemask(), live_seg);
+    if (live && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&seg_live[live_seg], __popc(peers));
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -392,23 +406,29 @@ nms_output_kernel(const unsigned long long* __restrict__ keys, const uint32_t* _
 struct NmsBuffers {
   unsigned long long* keys;
   uint32_t* vals;
+  unsigned long long* keys2;
+  uint32_t* vals2;
   float4* sbox;
   uint32_t* runkey;
   unsigned long long* mask;
   unsigned long long* keepbits;
   unsigned long long* diag_cols;
   uint32_t* seg_max;
+  int32_t* seg_live;
 };
 
 static size_t carve(Workspace& ws, NmsBuffers& b, int n_total, int n_seg, int max_seg_len) {
   const int P = next_pow2(n_total > 0 ? n_total : 1);
   b.keys = ws.take<unsigned long long>(P);
   b.vals = ws.take<uint32_t>(P);
+  b.keys2 = ws.take<unsigned long long>(P);    // out-of-place buffers of the rank sort
+  b.vals2 = ws.take<uint32_t>(P);
   b.sbox = ws.take<float4>(P);
   b.runkey = ws.take<uint32_t>(P);
   b.keepbits = ws.take<unsigned long long>(P / 64 + 1);
   b.diag_cols = ws.take<unsigned long long>(P);
   b.seg_max = ws.take<uint32_t>(n_seg > 0 ? n_seg : 1);
+  b.seg_live = ws.take<int32_t>(2 * (size_t)(n_seg > 0 ? n_seg : 1));   // live per segment: first / second sort
   b.mask = ws.take<unsigned long long>((size_t)(n_total > 0 ? n_total : 1) * nms_mask_row_words(max_seg_len));
   return ws.used;
 }
@@ -452,11 +472,22 @@ extern "C" int dgod_nms_batched(const float* boxes, const float* scores, const i
   DGOD_CUDA(cudaMemsetAsync(b.keepbits, 0, (size_t)(P / 64 + 1) * sizeof(unsigned long long), st));
   if (offset_mode) DGOD_CUDA(cudaMemsetAsync(b.seg_max, 0, (size_t)n_seg * sizeof(uint32_t), st));
 
+  // segments of a training step (4-8 k candidates) are ordered by one rank-sort launch; very long
+  // segments take the bitonic network
+  const bool use_rank = max_seg_len <= kRankSortMaxSeg && n_seg <= kRankSortMaxNseg;
+  if (use_rank) DGOD_CUDA(cudaMemsetAsync(b.seg_live, 0, 2 * (size_t)n_seg * sizeof(int32_t), st));
   nms_prepare_kernel<<<cdiv(P, 256), 256, 0, st>>>(boxes, scores, groups, valid, seg_offsets, n_seg,
                                                    n_total, P, offset_mode, b.keys, b.vals,
-                                                   b.seg_max, status);
+                                                   b.seg_max, use_rank ? b.seg_live : nullptr, status);
   DGOD_LAUNCHED();
-  int rc = bitonic_sort(b.keys, b.vals, P, st);
+  int rc;
+  if (use_rank) {
+    rc = rank_sort(b.keys, b.vals, seg_offsets, nullptr, b.seg_live, n_seg, n_total, P, max_seg_len, b.keys2, b.vals2, st);
+    std::swap(b.keys, b.keys2);
+    std::swap(b.vals, b.vals2);
+  } else {
+    rc = bitonic_sort(b.keys, b.vals, P, st);
+  }
   if (rc) return rc;
   nms_gather_kernel<<<cdiv(P, 256), 256, 0, st>>>(boxes, groups, b.keys, b.vals, b.seg_max, P,
                                                   offset_mode, b.sbox, b.runkey);
@@ -466,9 +497,16 @@ extern "C" int dgod_nms_batched(const float* boxes, const float* scores, const i
   if (rc) return rc;
   rc = launch_nms_scan(b.mask, b.diag_cols, b.runkey, nullptr, n_total, max_seg_len, b.keepbits, nullptr, nullptr, st);
   if (rc) return rc;
-  nms_rekey_kernel<<<cdiv(P, 256), 256, 0, st>>>(b.keys, b.keepbits, P);
+  nms_rekey_kernel<<<cdiv(P, 256), 256, 0, st>>>(b.keys, b.keepbits, P, use_rank ? b.seg_live + n_seg : nullptr);
   DGOD_LAUNCHED();
-  rc = bitonic_sort(b.keys, b.vals, P, st);
+  if (use_rank) {
+    // the input is the first sort's output: segment s now lives in the live range of s
+    rc = rank_sort(b.keys, b.vals, seg_offsets, b.seg_live, b.seg_live + n_seg, n_seg, n_total, P, max_seg_len, b.keys2, b.vals2, st);
+    std::swap(b.keys, b.keys2);
+    std::swap(b.vals, b.vals2);
+  } else {
+    rc = bitonic_sort(b.keys, b.vals, P, st);
+  }
   if (rc) return rc;
   nms_output_kernel<<<cdiv(P, 256), 256, 0, st>>>(b.keys, b.vals, seg_offsets, P, out_stride,
                                                   keep_out, keep_count);
