@@ -301,7 +301,7 @@ def run_b200(args):
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_sample(steps: int, warmup: int):
+def cpu_reference_sample(steps: int, warmup: int, n_dom: int = 2):
     """The reference's CPU path (oracle/ref_dgfrcnn.py on stock torchvision CPU ops), bounded:
     one step = one full dg mode cycle at batch 1 (8 images of 3x800x1333), all host threads."""
     import torch
@@ -309,8 +309,8 @@ def cpu_reference_sample(steps: int, warmup: int):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    model = RefDGFRCNN(9, 1, REG_WEIGHTS, 2).train()
-    batches = synthetic_batches(4, 1, 2, 0)
+    model = RefDGFRCNN(9, 1, REG_WEIGHTS, n_dom).train()
+    batches = synthetic_batches(4, 1, n_dom, 0)
     calibrate(model, batches[0][0] + batches[1][0])
     opt = model.configure_optimizer(lr=BENCH_LR)
 
@@ -342,7 +342,8 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = min(args.steps, 3), min(args.warmup, 1)
-    r = cpu_reference_sample(steps, warmup)
+    n_dom = args.domains or (2 if args.gpus == 1 else 3)        # same rule as the CUDA arm
+    r = cpu_reference_sample(steps, warmup, n_dom)
     out = {
         "impl": "reference", "metric": "DGFRCNN dg train img/s", "value": round(r["value"], 4), "unit": "img/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(r["ms_per_step"], 1),
@@ -350,7 +351,7 @@ def run_reference(args):
         "config": {"workload": "DGFRCNN dg mode on the host CPU: step = one 8-training-step mode cycle at batch 1 "
                                f"(bounded sample of the GPU arm's workload, same 3x{IMG_H}x{IMG_W} synthetic images, "
                                "same detector and schedule); steps/warmup capped at 3/1 to stay within minutes",
-                   "batch_per_gpu": 1, "domains": 2, "parallelism": "cpu"},
+                   "batch_per_gpu": 1, "domains": n_dom, "parallelism": "cpu"},
         "cpu_baseline": r["cpu_baseline"],
         "e2e": {"value": round(r["value"], 4), "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
