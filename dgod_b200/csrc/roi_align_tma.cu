@@ -10,7 +10,7 @@
 //   msroi_plan_kernel   one warp per RoI: level mapping, sampling taps (the same axis_tap() the
 //                       exact kernels use, i.e. TV's out-of-range skip rule and border clamp), the
 //                       compact list of live feature rows, the separable weight tables.  The result
-//                       is a 3.3 KB "plan" record per RoI in the caller's workspace, so the
+//                       is a 4.1 KB "plan" record per RoI in the caller's workspace, so the
 //                       streaming kernels below do no per-RoI arithmetic at all.
 //   msroi_fwd_tma       one CTA per RoI, warp-specialised.  A producer lane bulk-loads the plan and
 //                       streams the live footprint rows through a ring of up to 8 stages
@@ -24,10 +24,10 @@
 //                       memory and add it to the gradient map with ONE cp.reduce.async.bulk (SASS
 //                       UBLKRED): the L2 does the read-modify-write.  (The per-tap kernel issued 16
 //                       RED per output element and was bound by the SM's RED issue rate, ~1.3
-//                       cycles per lane.)  Every CTA zero-fills its share of image b+1 before it
-//                       starts on image b's RoIs and an RoI of image b waits for zero_done[b], so
-//                       the gradient maps need no memset and the zero lines are still dirty in L2
-//                       when the reductions arrive.
+//                       cycles per lane.)  A third warp role zero-fills this CTA's share of the
+//                       gradient maps image by image, a bounded distance ahead of the consumers; an
+//                       RoI of image b waits for zero_done[b] == gridDim.x, so the maps need no
+//                       memset and no grid-wide barrier.
 //
 // Arithmetic: bilinear pooling is separable.  With A_y[y][ph] = sum over the sampling rows of bin
 // ph of the weight they put on feature row y (and the column taps likewise),
@@ -156,20 +156,25 @@ struct alignas(128) RoiPlan {
   int level, batch;
   int x_first;           // span mode: first column of the span
   float inv_count;       // 1 / (sr*sr)
-  int pad[8];
+  int sparse_rows;       // every live row puts weight on <= 3 consecutive bins ph (window start row_ph0[i])
+  int sparse_cols;       // span mode: every span column puts weight on <= 3 consecutive bins pw
+  int pad[6];
   // lists (128 B)
   short rows[kMaxLive];                 // live feature rows, ascending
   short slot_x[kMaxSamp];               // slot mode: first pixel of sample s
   signed char slot_of[kMaxSamp + 2];    // slot mode: compact slot index of a valid sample, -1 otherwise
   unsigned char slot_two[kMaxSamp + 2]; // slot mode: the slot holds two pixels (xhi != xlo)
   unsigned char pad2[12];
+  unsigned char row_ph0[kMaxLive];      // first bin of live row i's 3-bin window (0..4)
+  unsigned char col_start[8];           // span columns [col_start[o], col_start[o+1]) use the window pw = o..o+2
+  unsigned char pad3[28];
   // tables
   ColTap xs[kMaxSamp];                  // 448 B   column taps of every sample
   float2 ay2[kMaxLive][8];              // 1792 B  (a,a) of the live rows, list order, unscaled
-  float ax[kSpanMax][8];                // 896 B   backward, span mode: dense A_x of the span's columns
+  float2 ax2[kSpanMax][8];              // 1792 B  backward, span mode: (w,w) pairs of the dense A_x of the span's columns
 };
 static_assert(sizeof(RoiPlan) % 128 == 0, "plans are moved with bulk copies");
-constexpr int kPlanFwdBytes = (int)offsetof(RoiPlan, ax);       // the forward kernel loads this prefix
+constexpr int kPlanFwdBytes = (int)offsetof(RoiPlan, ax2);       // the forward kernel loads this prefix
 constexpr int kPlanBwdBytes = (int)sizeof(RoiPlan);
 static_assert(kPlanFwdBytes % 16 == 0, "bulk copy granularity");
 
@@ -306,10 +311,53 @@ msroi_plan_kernel(const RoiDev g, const float* __restrict__ rois, int n_rois, Ro
     const float a = (i < n_rows && p < kP) ? axis_weight(t.ylo, t.yhi, t.yl, t.yh, t.rows[i], p, sr) : 0.f;
     P.ay2[i][p] = make_float2(a, a);
   }
+  {  // 3-bin windows of the live rows: the separable passes then need 3 instead of 7 multiply-adds
+    bool ok = true;
+    if (lane < n_rows) {
+      int first = kP, last = -1;
+      for (int p = 0; p < kP; ++p)
+        if (axis_weight(t.ylo, t.yhi, t.yl, t.yh, t.rows[lane], p, sr) != 0.f) { first = min(first, p); last = p; }
+      if (last < 0) { first = 0; last = 0; }
+      ok = last - first <= 2;
+      P.row_ph0[lane] = (unsigned char)min(first, kP - 3);
+    }
+    const unsigned all_ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) P.sparse_rows = all_ok ? 1 : 0;
+  }
+  if (!slot_mode) {  // columns of the span: windows are non-decreasing in x, so they form 5 contiguous ranges
+    bool ok = true;
+    int w0 = -1;                                   // -1: a gap column inside the span (no weight at all)
+    if (lane < span) {
+      int first = kP, last = -1;
+      for (int p = 0; p < kP; ++p)
+        if (axis_weight(t.xlo, t.xhi, t.xl, t.xh, x_first + lane, p, sr) != 0.f) { first = min(first, p); last = p; }
+      if (last >= 0) {
+        ok = last - first <= 2;
+        w0 = min(first, kP - 3);
+      }
+    }
+    int pm = w0;                                   // inclusive prefix maximum: gap columns inherit a neighbour's window
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, pm, d);
+      if (lane >= d) pm = max(pm, o);
+    }
+    ok = ok && (w0 < 0 || w0 == pm);               // window starts must not decrease
+    pm = max(pm, 0);
+    const unsigned all_ok = __all_sync(0xffffffffu, ok);
+    for (int o = 0; o < 8; ++o) {                  // col_start[o] = number of span columns with window start < o
+      const unsigned m = __ballot_sync(0xffffffffu, lane < span && pm < o);
+      if (lane == 0) P.col_start[o] = (unsigned char)(o >= 5 ? span : __popc(m));
+    }
+    if (lane == 0) P.sparse_cols = all_ok ? 1 : 0;
+  } else if (lane == 0) {
+    P.sparse_cols = 0;
+  }
   if (want_ax && !slot_mode) {
     for (int e = lane; e < kSpanMax * 8; e += 32) {
       const int i = e >> 3, p = e & 7;
-      P.ax[i][p] = (i < span && p < kP) ? axis_weight(t.xlo, t.xhi, t.xl, t.xh, x_first + i, p, sr) : 0.f;
+      const float wgt = (i < span && p < kP) ? axis_weight(t.xlo, t.xhi, t.xl, t.xh, x_first + i, p, sr) : 0.f;
+      P.ax2[i][p] = make_float2(wgt, wgt);
     }
   }
 }
@@ -462,24 +510,27 @@ msroi_fwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, int n_ro
 struct alignas(16) BwdSync {
   alignas(8) unsigned long long plan_full[kPlanBufBwd], plan_empty[kPlanBufBwd];
   alignas(8) unsigned long long g_full, g_empty;
+  volatile int cur_img;                 // image the consumers are working on (throttles the zero-fill warp)
 };
+constexpr int kZeroAhead = 2;           // the zero-fill warp runs at most this many images ahead
 
 template <typename T, int C> struct BwdCfg {
   static constexpr int kStaging = C * kNB * (int)sizeof(T);                       // gradient block of one RoI
   static constexpr int kPlans = kPlanBufBwd * kPlanBwdBytes;
   static constexpr int kRowBytesMax = kSpanMax * C * (int)sizeof(T);
-  static constexpr int kAvail = kSmemBudget - kStaging - kPlans - (int)sizeof(BwdSync) - 256;
-  static constexpr int kRing = 2 * kRowBytesMax;                                  // two fixed row buffers
+  // 2 CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2 = 115 712 B of static + dynamic shared memory each
+  static constexpr int kAvail = 115456 - kStaging - kPlans - (int)sizeof(BwdSync) - 320;
+  static constexpr int kRing = (kAvail / 1024) * 1024 < 4 * kRowBytesMax ? (kAvail / 1024) * 1024 : 4 * kRowBytesMax;
   static constexpr int kSmem = kStaging + kPlans + kRing;
-  static_assert(kRing <= (kAvail / 1024) * 1024, "shared-memory budget for 2 CTAs per SM");
+  static_assert(kRing >= kRowBytesMax, "the row ring must hold the widest row");
 };
 
 template <typename T, int C, int SR>
-__global__ void __launch_bounds__(C / 2 + 32, 2)
+__global__ void __launch_bounds__(C / 2 + 64, 2)
 msroi_bwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, const T* __restrict__ grad_out, int n_rois,
                      int* __restrict__ zero_done) {
   constexpr int NS = kP * SR;
-  constexpr int NC = C / 2;
+  constexpr int NC = C / 2;             // consumer threads; then one producer warp and one zero-fill warp
   constexpr int PIX = C * (int)sizeof(T);
   constexpr int RING = BwdCfg<T, C>::kRing;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -499,6 +550,7 @@ msroi_bwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, const T*
     mbar_init(&f.g_full, 1);
     mbar_init(&f.g_empty, NC / 32);
     mbar_fence_init();
+    f.cur_img = nj > 0 ? 0 : g.B;       // a CTA without RoIs never throttles its zero-fill warp
   }
   __syncthreads();
 
@@ -515,22 +567,29 @@ msroi_bwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, const T*
       mbar_expect_tx(&f.g_full, (unsigned)(C * kNB * sizeof(T)));
       bulk_load_hint(staging, grad_out + k * C * kNB, (unsigned)(C * kNB * sizeof(T)), &f.g_full, stream);
     }
-  } else if (tid < NC) {
-    // ------------------------------------------------------------------ consumers: channels 2*tid, 2*tid+1
-    int zeroed_upto = -1, cur_img = -1;
-    const unsigned long long keep = policy_evict_last();   // gradient maps of the images in flight stay in L2
-    auto zero_share = [&](int b) {       // this CTA's share of image b's gradient maps
+  } else if (tid >= NC + 32) {
+    // ------------------------------------------------------------------ zero-fill warp
+    // This CTA's share of every image's gradient maps, image by image, at most kZeroAhead images ahead
+    // of the consumers; zero_done[b] counts the CTAs that finished image b.  All CTAs are co-resident
+    // (cooperative launch), so a consumer waiting for zero_done[b] == gridDim.x cannot deadlock.
+    const int lane = tid - NC - 32;
+    const unsigned long long keep = policy_evict_last();
+    for (int b = 0; b < g.B; ++b) {
+      while (f.cur_img < b - kZeroAhead) __nanosleep(200);
       for (int l = 0; l < g.n_levels; ++l) {
         const size_t n16 = (size_t)g.H[l] * g.W[l] * C * sizeof(T) / 16;
         uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<T*>(g.gfeat[l]) + (size_t)b * g.H[l] * g.W[l] * C);
-        for (size_t i = (size_t)blockIdx.x * NC + tid; i < n16; i += (size_t)gridDim.x * NC) st_zero16_hint(p + i, keep);
+        for (size_t i = (size_t)blockIdx.x * 32 + lane; i < n16; i += (size_t)gridDim.x * 32) st_zero16_hint(p + i, keep);
       }
       asm volatile("fence.proxy.async.global;\n" ::: "memory");   // generic-proxy zeros before the bulk engine's RMW
       __threadfence();
-      consumer_barrier<NC>();
-      if (tid == 0) atomicAdd(&zero_done[b], 1);
-    };
-    unsigned issued = 0;                 // row reductions committed by thread 0 (ring position)
+      __syncwarp();
+      if (lane == 0) atomicAdd(&zero_done[b], 1);
+    }
+  } else if (tid < NC) {
+    // ------------------------------------------------------------------ consumers: channels 2*tid, 2*tid+1
+    const unsigned long long keep = policy_evict_last();   // gradient maps of the images in flight stay in L2
+    int cur_img = -1;
     for (int j = 0; j < nj; ++j) {
       const int s = j % kPlanBufBwd;
       mbar_wait(&f.plan_full[s], (unsigned)(j / kPlanBufBwd) & 1u);
@@ -549,17 +608,19 @@ msroi_bwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, const T*
       if ((tid & 31) == 0) mbar_arrive(&f.g_empty);
       if (n_rows) {
         const int b = P.batch;
-        while (zeroed_upto < min(b + 1, g.B - 1)) zero_share(++zeroed_upto);
-        if (b != cur_img) {
-          cur_img = b;
-          if (tid == 0) {
+        const int slot_mode = P.slot_mode, row_px = P.row_px, W = g.W[P.level];
+        const unsigned row_bytes = (unsigned)row_px * PIX;
+        const int n_buf = min(4, RING / (int)row_bytes);            // 1..4 row buffers of this RoI's row size
+        if (tid == 0) {
+          bulk_wait_read<0>();           // the previous RoI's rows (other buffer geometry) have been read
+          if (b != cur_img) {
+            f.cur_img = b;
             while (atomicAdd(&zero_done[b], 0) < (int)gridDim.x) __nanosleep(100);
             __threadfence();
           }
-          consumer_barrier<NC>();
         }
-        const int slot_mode = P.slot_mode, row_px = P.row_px, W = g.W[P.level];
-        const unsigned row_bytes = (unsigned)row_px * PIX;
+        cur_img = b;
+        consumer_barrier<NC>();
         T* __restrict__ img = reinterpret_cast<T*>(g.gfeat[P.level]) + (size_t)b * g.H[P.level] * W * C;
         for (int i = 0; i < n_rows; ++i) {
           float2 tq[kP];
@@ -571,21 +632,24 @@ msroi_bwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, const T*
 #pragma unroll
             for (int pw = 0; pw < kP; ++pw) tq[pw] = __ffma2_rn(a, gr[ph * kP + pw], tq[pw]);
           }
-          unsigned char* buf = ring + (size_t)(issued & 1u) * (RING / 2);     // two fixed buffers of the widest row
+          unsigned char* buf = ring + (size_t)(i % n_buf) * row_bytes;
           unsigned char* __restrict__ row = buf + tid * 2 * (int)sizeof(T);
           if (!slot_mode) {
 #pragma unroll 2
             for (int x = 0; x < row_px; ++x) {
-              const float4 w0 = *reinterpret_cast<const float4*>(&P.ax[x][0]);
-              const float4 w1 = *reinterpret_cast<const float4*>(&P.ax[x][4]);
-              float2 v = __fmul2_rn(make_float2(w0.x, w0.x), tq[0]);
-              v = __ffma2_rn(make_float2(w0.y, w0.y), tq[1], v);
-              v = __ffma2_rn(make_float2(w0.z, w0.z), tq[2], v);
-              v = __ffma2_rn(make_float2(w0.w, w0.w), tq[3], v);
-              v = __ffma2_rn(make_float2(w1.x, w1.x), tq[4], v);
-              v = __ffma2_rn(make_float2(w1.y, w1.y), tq[5], v);
-              v = __ffma2_rn(make_float2(w1.z, w1.z), tq[6], v);
-              st_pair<T>(row + x * PIX, v);
+              const float4 w01 = *reinterpret_cast<const float4*>(&P.ax2[x][0]);   // (w0,w0,w1,w1)
+              const float4 w23 = *reinterpret_cast<const float4*>(&P.ax2[x][2]);
+              const float4 w45 = *reinterpret_cast<const float4*>(&P.ax2[x][4]);
+              const float2 w6 = P.ax2[x][6];
+              // two independent accumulation chains per pixel
+              float2 va = __fmul2_rn(make_float2(w01.x, w01.y), tq[0]);
+              float2 vb = __fmul2_rn(make_float2(w01.z, w01.w), tq[1]);
+              va = __ffma2_rn(make_float2(w23.x, w23.y), tq[2], va);
+              vb = __ffma2_rn(make_float2(w23.z, w23.w), tq[3], vb);
+              va = __ffma2_rn(make_float2(w45.x, w45.y), tq[4], va);
+              vb = __ffma2_rn(make_float2(w45.z, w45.w), tq[5], vb);
+              va = __ffma2_rn(w6, tq[6], va);
+              st_pair<T>(row + x * PIX, __fadd2_rn(va, vb));
             }
           } else {
 #pragma unroll
@@ -601,7 +665,11 @@ msroi_bwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, const T*
             }
           }
           fence_proxy_async_smem();             // generic-proxy writes -> visible to the bulk engine
-          if (tid == 0) bulk_wait_read<0>();    // the buffer the NEXT row will write has been read
+          if (tid == 0) {                       // the buffer the NEXT row will write must have been read
+            if (n_buf == 2) bulk_wait_read<0>();
+            else if (n_buf == 3) bulk_wait_read<1>();
+            else if (n_buf == 4) bulk_wait_read<2>();
+          }
           consumer_barrier<NC>();
           if (tid == 0) {
             const size_t yw = (size_t)P.rows[i] * W;
@@ -615,14 +683,19 @@ msroi_bwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, const T*
             }
             bulk_commit();
           }
-          ++issued;
+          if (n_buf == 1) {                     // a single buffer: its reduction must be read before it is rewritten
+            if (tid == 0) bulk_wait_read<0>();
+            consumer_barrier<NC>();
+          }
         }
       }
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(&f.plan_empty[s]);
     }
-    while (zeroed_upto < g.B - 1) zero_share(++zeroed_upto);   // images this CTA never reached
-    if (tid == 0) bulk_wait_read<0>();
+    if (tid == 0) {
+      f.cur_img = g.B;                    // release the zero-fill warp for the remaining images
+      bulk_wait_read<0>();
+    }
   }
 }
 
@@ -695,7 +768,7 @@ static int launch_bwd_tma(const RoiDev& g, const void* grad_out, const float* ro
     DGOD_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     DGOD_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     DGOD_CUDA(cudaFuncSetAttribute(msroi_bwd_tma_kernel<T, C, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    DGOD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msroi_bwd_tma_kernel<T, C, SR>, C / 2 + 32, kSmem));
+    DGOD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msroi_bwd_tma_kernel<T, C, SR>, C / 2 + 64, kSmem));
     n_cta = n_sm * per_sm;
     init = true;
   }
@@ -713,7 +786,7 @@ static int launch_bwd_tma(const RoiDev& g, const void* grad_out, const float* ro
   const RoiPlan* cplans = plans;
   RoiDev gg = g;
   void* args[] = {(void*)&gg, (void*)&cplans, (void*)&go, (void*)&n_rois, (void*)&zero_done};
-  DGOD_CUDA(cudaLaunchCooperativeKernel((const void*)msroi_bwd_tma_kernel<T, C, SR>, dim3(n_cta), dim3(C / 2 + 32), args, kSmem, st));
+  DGOD_CUDA(cudaLaunchCooperativeKernel((const void*)msroi_bwd_tma_kernel<T, C, SR>, dim3(n_cta), dim3(C / 2 + 64), args, kSmem, st));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return DGOD_OK;
 }
