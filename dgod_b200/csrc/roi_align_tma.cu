@@ -156,8 +156,8 @@ struct alignas(128) RoiPlan {
   int level, batch;
   int x_first;           // span mode: first column of the span
   float inv_count;       // 1 / (sr*sr)
-  int sparse_rows;       // every live row puts weight on <= 3 consecutive bins ph (window start row_ph0[i])
-  int sparse_cols;       // span mode: every span column puts weight on <= 3 consecutive bins pw
+  int sparse_rows;       // backward: every live row puts weight on <= 3 consecutive bins ph (ays)
+  int sparse_cols;       // backward, span mode: every span column puts weight on <= 3 consecutive bins pw (axs, col_start)
   int pad[6];
   // lists (128 B)
   short rows[kMaxLive];                 // live feature rows, ascending
@@ -165,16 +165,18 @@ struct alignas(128) RoiPlan {
   signed char slot_of[kMaxSamp + 2];    // slot mode: compact slot index of a valid sample, -1 otherwise
   unsigned char slot_two[kMaxSamp + 2]; // slot mode: the slot holds two pixels (xhi != xlo)
   unsigned char pad2[12];
-  unsigned char row_ph0[kMaxLive];      // first bin of live row i's 3-bin window (0..4)
-  unsigned char col_start[8];           // span columns [col_start[o], col_start[o+1]) use the window pw = o..o+2
-  unsigned char pad3[28];
+  unsigned char col_start[8];           // span columns [col_start[o], col_start[o+1]) draw on bins pw = o..o+2 (sparse_cols)
+  unsigned char pad3[56];
   // tables
   ColTap xs[kMaxSamp];                  // 448 B   column taps of every sample
   float2 ay2[kMaxLive][8];              // 1792 B  (a,a) of the live rows, list order, unscaled
-  float2 ax2[kSpanMax][8];              // 1792 B  backward, span mode: (w,w) pairs of the dense A_x of the span's columns
+  // backward only
+  float4 ays[kMaxLive];                 // 448 B   sparse_rows: (A_y[p0], A_y[p0+1], A_y[p0+2], bits of p0) of live row i
+  float4 axs[kSpanMax + 4];             // 512 B   sparse_cols: the three weights of span column x (+ zero rows: the loop prefetches)
+  float ax[kSpanMax + 4][8];            // 1024 B  span mode, dense A_x of the span's columns (+ zero rows)
 };
 static_assert(sizeof(RoiPlan) % 128 == 0, "plans are moved with bulk copies");
-constexpr int kPlanFwdBytes = (int)offsetof(RoiPlan, ax2);       // the forward kernel loads this prefix
+constexpr int kPlanFwdBytes = (int)offsetof(RoiPlan, ays);       // the forward kernel loads this prefix
 constexpr int kPlanBwdBytes = (int)sizeof(RoiPlan);
 static_assert(kPlanFwdBytes % 16 == 0, "bulk copy granularity");
 
@@ -311,6 +313,7 @@ msroi_plan_kernel(const RoiDev g, const float* __restrict__ rois, int n_rois, Ro
     const float a = (i < n_rows && p < kP) ? axis_weight(t.ylo, t.yhi, t.yl, t.yh, t.rows[i], p, sr) : 0.f;
     P.ay2[i][p] = make_float2(a, a);
   }
+  if (!want_ax) return;                // the forward kernel needs nothing below
   {  // 3-bin windows of the live rows: the separable passes then need 3 instead of 7 multiply-adds
     bool ok = true;
     if (lane < n_rows) {
@@ -319,12 +322,15 @@ msroi_plan_kernel(const RoiDev g, const float* __restrict__ rois, int n_rois, Ro
         if (axis_weight(t.ylo, t.yhi, t.yl, t.yh, t.rows[lane], p, sr) != 0.f) { first = min(first, p); last = p; }
       if (last < 0) { first = 0; last = 0; }
       ok = last - first <= 2;
-      P.row_ph0[lane] = (unsigned char)min(first, kP - 3);
+      const int p0 = min(first, kP - 3);
+      P.ays[lane] = make_float4(axis_weight(t.ylo, t.yhi, t.yl, t.yh, t.rows[lane], p0, sr),
+                                axis_weight(t.ylo, t.yhi, t.yl, t.yh, t.rows[lane], p0 + 1, sr),
+                                axis_weight(t.ylo, t.yhi, t.yl, t.yh, t.rows[lane], p0 + 2, sr), __int_as_float(p0));
     }
     const unsigned all_ok = __all_sync(0xffffffffu, ok);
     if (lane == 0) P.sparse_rows = all_ok ? 1 : 0;
   }
-  if (!slot_mode) {  // columns of the span: windows are non-decreasing in x, so they form 5 contiguous ranges
+  if (!slot_mode) {  // columns of the span: window starts are non-decreasing in x, so they form 5 contiguous ranges
     bool ok = true;
     int w0 = -1;                                   // -1: a gap column inside the span (no weight at all)
     if (lane < span) {
@@ -347,17 +353,20 @@ msroi_plan_kernel(const RoiDev g, const float* __restrict__ rois, int n_rois, Ro
     const unsigned all_ok = __all_sync(0xffffffffu, ok);
     for (int o = 0; o < 8; ++o) {                  // col_start[o] = number of span columns with window start < o
       const unsigned m = __ballot_sync(0xffffffffu, lane < span && pm < o);
-      if (lane == 0) P.col_start[o] = (unsigned char)(o >= 5 ? span : __popc(m));
+      if (lane == 0) P.col_start[o] = (unsigned char)(o >= kP - 2 ? span : __popc(m));
     }
     if (lane == 0) P.sparse_cols = all_ok ? 1 : 0;
+    P.axs[lane] = lane < span ? make_float4(axis_weight(t.xlo, t.xhi, t.xl, t.xh, x_first + lane, pm, sr),
+                                            axis_weight(t.xlo, t.xhi, t.xl, t.xh, x_first + lane, pm + 1, sr),
+                                            axis_weight(t.xlo, t.xhi, t.xl, t.xh, x_first + lane, pm + 2, sr), 0.f)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);      // kSpanMax + 4 = 32 entries
   } else if (lane == 0) {
     P.sparse_cols = 0;
   }
-  if (want_ax && !slot_mode) {
-    for (int e = lane; e < kSpanMax * 8; e += 32) {
+  if (!slot_mode) {
+    for (int e = lane; e < (kSpanMax + 4) * 8; e += 32) {
       const int i = e >> 3, p = e & 7;
-      const float wgt = (i < span && p < kP) ? axis_weight(t.xlo, t.xhi, t.xl, t.xh, x_first + i, p, sr) : 0.f;
-      P.ax2[i][p] = make_float2(wgt, wgt);
+      P.ax[i][p] = (i < span && p < kP) ? axis_weight(t.xlo, t.xhi, t.xl, t.xh, x_first + i, p, sr) : 0.f;
     }
   }
 }
@@ -372,6 +381,36 @@ template <typename T> __device__ __forceinline__ void st_pair(unsigned char* p, 
 template <> __device__ __forceinline__ void st_pair<float>(unsigned char* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
 template <> __device__ __forceinline__ void st_pair<__nv_bfloat16>(unsigned char* p, float2 v) {
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y);
+}
+
+// Shared-memory accesses of the hot loops go through 32-bit shared-window addresses computed once per
+// row.  (With generic pointers into the dynamic shared array the compiler rematerialises the window
+// base — S2UR SR_CgaCtaId + ULEA — in front of every predicated store; ncu showed that pair as the
+// top stall of the backward row loop.)  The asm statements are volatile without a memory clobber:
+// they keep their order among themselves and relative to the mbarrier / fence statements.
+__device__ __forceinline__ float4 lds_f4(unsigned a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+template <typename T> __device__ __forceinline__ float2 lds_pair(unsigned a);
+template <> __device__ __forceinline__ float2 lds_pair<float>(unsigned a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+template <> __device__ __forceinline__ float2 lds_pair<__nv_bfloat16>(unsigned a) {
+  unsigned u;
+  asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(u) : "r"(a));
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+template <typename T> __device__ __forceinline__ void sts_pair(unsigned a, float2 v);
+template <> __device__ __forceinline__ void sts_pair<float>(unsigned a, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};\n" ::"r"(a), "f"(v.x), "f"(v.y));
+}
+template <> __device__ __forceinline__ void sts_pair<__nv_bfloat16>(unsigned a, float2 v) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+  asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(a), "r"(*reinterpret_cast<const unsigned*>(&h)));
 }
 
 // ================================================================================================
@@ -432,8 +471,11 @@ msroi_fwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, int n_ro
   if (n_rows) {
     const unsigned row_bytes = (unsigned)P.row_px * PIX;                // multiple of 128, <= 28 KB
     const int n_stage = min(kStagesMax, RING / (int)row_bytes);        // >= 3
-    if (tid == NC) {
-      // ---------------- producer lane
+    if (tid >= NC && tid < NC + n_stage) {
+      // ---------------- producer lanes: lane p owns ring stage p and streams rows p, p + n_stage, ...  (bulk copies
+      // issued by one thread complete one at a time, ~750 cycles each whatever their size —
+      // tools/microbench/bulk_load_issue.cu — while copies of different lanes overlap; one lane per stage also keeps
+      // every mbarrier's phases waited on strictly in order)
       const int slot_mode = P.slot_mode, W = g.W[P.level];
       const T* __restrict__ img = reinterpret_cast<const T*>(g.feat[P.level]) + (size_t)P.batch * g.H[P.level] * W * C;
       unsigned slot_total = 0;
@@ -442,8 +484,8 @@ msroi_fwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, int n_ro
           if (P.slot_of[sx] >= 0) slot_total += P.slot_two[sx] ? 2u * PIX : (unsigned)PIX;
       const T* __restrict__ span0 = img + (size_t)P.x_first * C;
       const unsigned long long keep = policy_evict_last();      // the image's maps are re-read by its other RoIs
-      for (int i = 0; i < n_rows; ++i) {
-        const int st = i % n_stage;
+      const int st = tid - NC;
+      for (int i = st; i < n_rows; i += n_stage) {
         if (i >= n_stage) mbar_wait(&f.empty[st], (unsigned)(i / n_stage - 1) & 1u);
         const size_t yw = (size_t)P.rows[i] * W;
         unsigned char* dst = ring + (size_t)st * row_bytes;
@@ -460,10 +502,12 @@ msroi_fwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, int n_ro
       }
     } else if (tid < NC) {
       // ---------------- consumers: thread owns channels 2*tid, 2*tid+1
+      const unsigned ring_s = smem_u32(ring) + (unsigned)tid * 2u * (unsigned)sizeof(T);
+      int st = 0;
+      unsigned phase = 0u;
       for (int i = 0; i < n_rows; ++i) {
-        const int st = i % n_stage;
-        mbar_wait(&f.full[st], (unsigned)(i / n_stage) & 1u);
-        const unsigned char* __restrict__ row = ring + (size_t)st * row_bytes + tid * 2 * (int)sizeof(T);
+        mbar_wait(&f.full[st], phase);
+        const unsigned row = ring_s + (unsigned)st * row_bytes;
         float2 rx[kP];
 #pragma unroll
         for (int p = 0; p < kP; ++p) rx[p] = make_float2(0.f, 0.f);
@@ -471,7 +515,7 @@ msroi_fwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, int n_ro
         for (int sx = 0; sx < NS; ++sx) {
           const uint2 o = *reinterpret_cast<const uint2*>(&P.xs[sx].off_lo);
           const float4 w = *reinterpret_cast<const float4*>(&P.xs[sx].hx);
-          const float2 v0 = ld_pair<T>(row + o.x), v1 = ld_pair<T>(row + o.y);
+          const float2 v0 = lds_pair<T>(row + o.x), v1 = lds_pair<T>(row + o.y);
           rx[sx / SR] = __ffma2_rn(make_float2(w.z, w.w), v1, __ffma2_rn(make_float2(w.x, w.y), v0, rx[sx / SR]));
         }
 #pragma unroll
@@ -482,6 +526,7 @@ msroi_fwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, int n_ro
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&f.empty[st]);       // this warp is done with stage st
+        if (++st == n_stage) { st = 0; phase ^= 1u; }
       }
     }
   }
@@ -507,12 +552,22 @@ msroi_fwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, int n_ro
 // ================================================================================================
 // Backward
 // ================================================================================================
+// Persistent, cooperative (all CTAs co-resident).  Per CTA: C/2 consumer threads (two adjacent
+// channels each, the RoI's 49 gradient values of both in registers), one driver lane that streams
+// plans / gradient blocks in and issues the row reductions, and one zero-fill warp.  Consumers and
+// the driver are decoupled: a warp hands a finished row over through an mbarrier (row_full) and goes
+// on with the next row as soon as the driver has published that the buffer it needs was read
+// (rows_released) — there is no CTA-wide barrier in the row loop.
+constexpr int kRowBars = 4;             // rows in flight per CTA (>= the largest number of row buffers)
+
 struct alignas(16) BwdSync {
   alignas(8) unsigned long long plan_full[kPlanBufBwd], plan_empty[kPlanBufBwd];
   alignas(8) unsigned long long g_full, g_empty;
-  volatile int cur_img;                 // image the consumers are working on (throttles the zero-fill warp)
+  alignas(8) unsigned long long row_full[kRowBars];
+  volatile unsigned rows_released;      // rows 0 .. rows_released-1 of this CTA have been read by the bulk engine
+  volatile int cur_img;                 // image the driver is working on (throttles the zero-fill warp)
 };
-constexpr int kZeroAhead = 2;           // the zero-fill warp runs at most this many images ahead
+constexpr int kZeroAhead = 2;           // the zero-fill warp runs at most this many images ahead (1: 10 % slower, 0: 75 %)
 
 template <typename T, int C> struct BwdCfg {
   static constexpr int kStaging = C * kNB * (int)sizeof(T);                       // gradient block of one RoI
@@ -520,17 +575,23 @@ template <typename T, int C> struct BwdCfg {
   static constexpr int kRowBytesMax = kSpanMax * C * (int)sizeof(T);
   // 2 CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2 = 115 712 B of static + dynamic shared memory each
   static constexpr int kAvail = 115456 - kStaging - kPlans - (int)sizeof(BwdSync) - 320;
-  static constexpr int kRing = (kAvail / 1024) * 1024 < 4 * kRowBytesMax ? (kAvail / 1024) * 1024 : 4 * kRowBytesMax;
+  static constexpr int kRing = (kAvail / 1024) * 1024 < kRowBars * kRowBytesMax ? (kAvail / 1024) * 1024 : kRowBars * kRowBytesMax;
   static constexpr int kSmem = kStaging + kPlans + kRing;
   static_assert(kRing >= kRowBytesMax, "the row ring must hold the widest row");
 };
+
+#ifdef DGOD_ROI_TIMING
+#define TICK(n) do { t1 = clock64(); tacc[n] += t1 - t0; t0 = t1; } while (0)
+#else
+#define TICK(n) do {} while (0)
+#endif
 
 template <typename T, int C, int SR>
 __global__ void __launch_bounds__(C / 2 + 64, 2)
 msroi_bwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, const T* __restrict__ grad_out, int n_rois,
                      int* __restrict__ zero_done) {
   constexpr int NS = kP * SR;
-  constexpr int NC = C / 2;             // consumer threads; then one producer warp and one zero-fill warp
+  constexpr int NC = C / 2;             // consumer threads; then the driver warp and the zero-fill warp
   constexpr int PIX = C * (int)sizeof(T);
   constexpr int RING = BwdCfg<T, C>::kRing;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -549,29 +610,88 @@ msroi_bwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, const T*
     }
     mbar_init(&f.g_full, 1);
     mbar_init(&f.g_empty, NC / 32);
+#pragma unroll
+    for (int i = 0; i < kRowBars; ++i) mbar_init(&f.row_full[i], NC / 32);
     mbar_fence_init();
+    f.rows_released = 0u;
     f.cur_img = nj > 0 ? 0 : g.B;       // a CTA without RoIs never throttles its zero-fill warp
   }
   __syncthreads();
 
   if (tid == NC) {
-    // ------------------------------------------------------------------ producer: plans and gradient blocks
+    // ------------------------------------------------------------------ driver lane
     const unsigned long long stream = policy_evict_first();
-    for (int j = 0; j < nj; ++j) {
-      const size_t k = (size_t)blockIdx.x + (size_t)j * gridDim.x;
+    const unsigned long long keep = policy_evict_last();   // gradient maps of the images in flight stay in L2
+    auto load_plan = [&](int j) {
       const int s = j % kPlanBufBwd;
-      if (j >= kPlanBufBwd) mbar_wait(&f.plan_empty[s], (unsigned)(j / kPlanBufBwd - 1) & 1u);
       mbar_expect_tx(&f.plan_full[s], kPlanBwdBytes);
-      bulk_load_hint(plan_buf + s * kPlanBwdBytes, plans + k, kPlanBwdBytes, &f.plan_full[s], stream);
-      if (j >= 1) mbar_wait(&f.g_empty, (unsigned)(j - 1) & 1u);    // consumers copied block j-1 to registers
+      bulk_load_hint(plan_buf + s * kPlanBwdBytes, plans + ((size_t)blockIdx.x + (size_t)j * gridDim.x), kPlanBwdBytes,
+                     &f.plan_full[s], stream);
+    };
+    auto load_block = [&](int j) {
       mbar_expect_tx(&f.g_full, (unsigned)(C * kNB * sizeof(T)));
-      bulk_load_hint(staging, grad_out + k * C * kNB, (unsigned)(C * kNB * sizeof(T)), &f.g_full, stream);
+      bulk_load_hint(staging, grad_out + ((size_t)blockIdx.x + (size_t)j * gridDim.x) * C * kNB, (unsigned)(C * kNB * sizeof(T)),
+                     &f.g_full, stream);
+    };
+    for (int j = 0; j < kPlanBufBwd && j < nj; ++j) load_plan(j);
+    if (nj > 0) load_block(0);
+    unsigned r = 0;                      // rows of this CTA, counted across RoIs
+    int cur_img = -1;
+    for (int j = 0; j < nj; ++j) {
+      const int s = j % kPlanBufBwd;
+      if (j + 1 < nj) {                  // consumers copy block j to registers first thing: refill the staging buffer
+        mbar_wait(&f.g_empty, (unsigned)j & 1u);
+        load_block(j + 1);
+      }
+      mbar_wait(&f.plan_full[s], (unsigned)(j / kPlanBufBwd) & 1u);
+      const RoiPlan& P = *reinterpret_cast<const RoiPlan*>(plan_buf + s * kPlanBwdBytes);
+      const int n_rows = P.n_rows;
+      if (n_rows) {
+        const int b = P.batch, slot_mode = P.slot_mode, W = g.W[P.level];
+        const unsigned row_bytes = (unsigned)P.row_px * PIX;
+        const int n_buf = min(kRowBars, RING / (int)row_bytes);
+        if (b != cur_img) {              // the image's maps must be zero before the first reduction lands
+          cur_img = b;
+          f.cur_img = b;
+          while (atomicAdd(&zero_done[b], 0) < (int)gridDim.x) __nanosleep(100);
+          __threadfence();
+        }
+        T* __restrict__ img = reinterpret_cast<T*>(g.gfeat[P.level]) + (size_t)b * g.H[P.level] * W * C;
+        for (int i = 0; i < n_rows; ++i, ++r) {
+          mbar_wait(&f.row_full[r % kRowBars], (r / kRowBars) & 1u);
+          unsigned char* buf = ring + (size_t)(i % n_buf) * row_bytes;
+          const size_t yw = (size_t)P.rows[i] * W;
+          if (!slot_mode) {
+            bulk_reduce_add_hint<T>(img + (yw + P.x_first) * C, buf, row_bytes, keep);
+          } else {
+            for (int sx = 0; sx < NS; ++sx)
+              if (P.slot_of[sx] >= 0)
+                bulk_reduce_add_hint<T>(img + (yw + P.slot_x[sx]) * C, buf + (size_t)P.slot_of[sx] * 2 * PIX,
+                                        P.slot_two[sx] ? 2u * PIX : (unsigned)PIX, keep);
+          }
+          bulk_commit();
+          if (n_buf == 1) {              // a single buffer (widest rows only): the row just issued must be read
+            bulk_wait_read<0>();
+            f.rows_released = r + 1u;
+          } else if (i + 1 < n_rows) {
+            bulk_wait_read<1>();         // every row but the one just issued has been read
+            f.rows_released = r;
+          }
+        }
+        bulk_wait_read<0>();             // the next RoI lays its buffers out differently: drain
+        f.rows_released = r;
+      }
+      if (j + kPlanBufBwd < nj) {        // recycle the plan slot once the consumers are done with it too
+        mbar_wait(&f.plan_empty[s], (unsigned)(j / kPlanBufBwd) & 1u);
+        load_plan(j + kPlanBufBwd);
+      }
     }
+    f.cur_img = g.B;                     // release the zero-fill warp for the remaining images
   } else if (tid >= NC + 32) {
     // ------------------------------------------------------------------ zero-fill warp
     // This CTA's share of every image's gradient maps, image by image, at most kZeroAhead images ahead
-    // of the consumers; zero_done[b] counts the CTAs that finished image b.  All CTAs are co-resident
-    // (cooperative launch), so a consumer waiting for zero_done[b] == gridDim.x cannot deadlock.
+    // of the reductions; zero_done[b] counts the CTAs that finished image b.  All CTAs are co-resident
+    // (cooperative launch), so a driver waiting for zero_done[b] == gridDim.x cannot deadlock.
     const int lane = tid - NC - 32;
     const unsigned long long keep = policy_evict_last();
     for (int b = 0; b < g.B; ++b) {
@@ -588,15 +708,22 @@ msroi_bwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, const T*
     }
   } else if (tid < NC) {
     // ------------------------------------------------------------------ consumers: channels 2*tid, 2*tid+1
-    const unsigned long long keep = policy_evict_last();   // gradient maps of the images in flight stay in L2
-    int cur_img = -1;
+#ifdef DGOD_ROI_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t0 = clock64(), t1;
+    const long long tstart = t0;
+#endif
+    unsigned r = 0, released = 0;
+    const unsigned ring_s = smem_u32(ring), plan_s = smem_u32(plan_buf);
     for (int j = 0; j < nj; ++j) {
       const int s = j % kPlanBufBwd;
       mbar_wait(&f.plan_full[s], (unsigned)(j / kPlanBufBwd) & 1u);
+      TICK(0);
       const RoiPlan& P = *reinterpret_cast<const RoiPlan*>(plan_buf + s * kPlanBwdBytes);
       const int n_rows = P.n_rows;
       // the gradient block: 49 values of this thread's two channels -> registers, pre-divided by count
       mbar_wait(&f.g_full, (unsigned)j & 1u);
+      TICK(1);
       float2 gr[kNB];
       {
         const float inv = P.inv_count;
@@ -606,23 +733,14 @@ msroi_bwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, const T*
       }
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(&f.g_empty);
+      TICK(2);
       if (n_rows) {
-        const int b = P.batch;
-        const int slot_mode = P.slot_mode, row_px = P.row_px, W = g.W[P.level];
+        const int slot_mode = P.slot_mode, row_px = P.row_px;
         const unsigned row_bytes = (unsigned)row_px * PIX;
-        const int n_buf = min(4, RING / (int)row_bytes);            // 1..4 row buffers of this RoI's row size
-        if (tid == 0) {
-          bulk_wait_read<0>();           // the previous RoI's rows (other buffer geometry) have been read
-          if (b != cur_img) {
-            f.cur_img = b;
-            while (atomicAdd(&zero_done[b], 0) < (int)gridDim.x) __nanosleep(100);
-            __threadfence();
-          }
-        }
-        cur_img = b;
-        consumer_barrier<NC>();
-        T* __restrict__ img = reinterpret_cast<T*>(g.gfeat[P.level]) + (size_t)b * g.H[P.level] * W * C;
-        for (int i = 0; i < n_rows; ++i) {
+        const int n_buf = min(kRowBars, RING / (int)row_bytes);            // 1..4 row buffers of this RoI's row size
+        const unsigned r0 = r;
+        for (int i = 0; i < n_rows; ++i, ++r) {
+          // ---- T: tq[pw] = sum_ph A_y[row][ph] * g[ph][pw]
           float2 tq[kP];
 #pragma unroll
           for (int pw = 0; pw < kP; ++pw) tq[pw] = make_float2(0.f, 0.f);
@@ -632,26 +750,19 @@ msroi_bwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, const T*
 #pragma unroll
             for (int pw = 0; pw < kP; ++pw) tq[pw] = __ffma2_rn(a, gr[ph * kP + pw], tq[pw]);
           }
-          unsigned char* buf = ring + (size_t)(i % n_buf) * row_bytes;
-          unsigned char* __restrict__ row = buf + tid * 2 * (int)sizeof(T);
-          if (!slot_mode) {
-#pragma unroll 2
-            for (int x = 0; x < row_px; ++x) {
-              const float4 w01 = *reinterpret_cast<const float4*>(&P.ax2[x][0]);   // (w0,w0,w1,w1)
-              const float4 w23 = *reinterpret_cast<const float4*>(&P.ax2[x][2]);
-              const float4 w45 = *reinterpret_cast<const float4*>(&P.ax2[x][4]);
-              const float2 w6 = P.ax2[x][6];
-              // two independent accumulation chains per pixel
-              float2 va = __fmul2_rn(make_float2(w01.x, w01.y), tq[0]);
-              float2 vb = __fmul2_rn(make_float2(w01.z, w01.w), tq[1]);
-              va = __ffma2_rn(make_float2(w23.x, w23.y), tq[2], va);
-              vb = __ffma2_rn(make_float2(w23.z, w23.w), tq[3], vb);
-              va = __ffma2_rn(make_float2(w45.x, w45.y), tq[4], va);
-              vb = __ffma2_rn(make_float2(w45.z, w45.w), tq[5], vb);
-              va = __ffma2_rn(w6, tq[6], va);
-              st_pair<T>(row + x * PIX, __fadd2_rn(va, vb));
+          TICK(3);
+          // ---- the buffer this row goes to must have been read by the bulk engine
+          {
+            const unsigned need = i >= n_buf ? r - (unsigned)n_buf + 1u : r0;
+            if (released < need) {
+              while ((released = f.rows_released) < need) __nanosleep(40);
+              __threadfence_block();
             }
-          } else {
+          }
+          TICK(4);
+          const unsigned row = ring_s + (unsigned)(i % n_buf) * row_bytes + (unsigned)tid * 2u * (unsigned)sizeof(T);
+          // ---- R: row[x] = sum_pw A_x[x][pw] * tq[pw]
+          if (slot_mode) {
 #pragma unroll
             for (int sx = 0; sx < NS; ++sx) {
               const int slot = P.slot_of[sx];
@@ -659,43 +770,53 @@ msroi_bwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, const T*
                 const float h = P.xs[sx].hx, l = P.xs[sx].lx;
                 const bool two = P.slot_two[sx];
                 const float w0 = two ? h : h + l;
-                st_pair<T>(row + (slot * 2) * PIX, __fmul2_rn(make_float2(w0, w0), tq[sx / SR]));
-                if (two) st_pair<T>(row + (slot * 2 + 1) * PIX, __fmul2_rn(make_float2(l, l), tq[sx / SR]));
+                sts_pair<T>(row + (unsigned)(slot * 2) * PIX, __fmul2_rn(make_float2(w0, w0), tq[sx / SR]));
+                if (two) sts_pair<T>(row + (unsigned)(slot * 2 + 1) * PIX, __fmul2_rn(make_float2(l, l), tq[sx / SR]));
               }
             }
-          }
-          fence_proxy_async_smem();             // generic-proxy writes -> visible to the bulk engine
-          if (tid == 0) {                       // the buffer the NEXT row will write must have been read
-            if (n_buf == 2) bulk_wait_read<0>();
-            else if (n_buf == 3) bulk_wait_read<1>();
-            else if (n_buf == 4) bulk_wait_read<2>();
-          }
-          consumer_barrier<NC>();
-          if (tid == 0) {
-            const size_t yw = (size_t)P.rows[i] * W;
-            if (!slot_mode) {
-              bulk_reduce_add_hint<T>(img + (yw + P.x_first) * C, buf, row_bytes, keep);
-            } else {
-              for (int sx = 0; sx < NS; ++sx)
-                if (P.slot_of[sx] >= 0)
-                  bulk_reduce_add_hint<T>(img + (yw + P.slot_x[sx]) * C, buf + (size_t)P.slot_of[sx] * 2 * PIX,
-                                          P.slot_two[sx] ? 2u * PIX : (unsigned)PIX, keep);
+          } else {
+            // two pixels per step; the weights of the next two are in flight while these are computed and stored
+            const unsigned axp = plan_s + (unsigned)s * kPlanBwdBytes + (unsigned)offsetof(RoiPlan, ax);
+            float4 wa0 = lds_f4(axp), wb0 = lds_f4(axp + 16), wa1 = lds_f4(axp + 32), wb1 = lds_f4(axp + 48);
+            for (int x = 0; x < row_px; x += 2) {
+              const unsigned nx = axp + (unsigned)(x + 2) * 32u;            // rows >= span are zero (kSpanMax + 4 rows)
+              const float4 na0 = lds_f4(nx), nb0 = lds_f4(nx + 16), na1 = lds_f4(nx + 32), nb1 = lds_f4(nx + 48);
+              float2 va = __fmul2_rn(make_float2(wa0.x, wa0.x), tq[0]);
+              float2 vb = __fmul2_rn(make_float2(wa0.y, wa0.y), tq[1]);
+              float2 vc = __fmul2_rn(make_float2(wa1.x, wa1.x), tq[0]);
+              float2 vd = __fmul2_rn(make_float2(wa1.y, wa1.y), tq[1]);
+              va = __ffma2_rn(make_float2(wa0.z, wa0.z), tq[2], va);
+              vb = __ffma2_rn(make_float2(wa0.w, wa0.w), tq[3], vb);
+              vc = __ffma2_rn(make_float2(wa1.z, wa1.z), tq[2], vc);
+              vd = __ffma2_rn(make_float2(wa1.w, wa1.w), tq[3], vd);
+              va = __ffma2_rn(make_float2(wb0.x, wb0.x), tq[4], va);
+              vb = __ffma2_rn(make_float2(wb0.y, wb0.y), tq[5], vb);
+              vc = __ffma2_rn(make_float2(wb1.x, wb1.x), tq[4], vc);
+              vd = __ffma2_rn(make_float2(wb1.y, wb1.y), tq[5], vd);
+              va = __ffma2_rn(make_float2(wb0.z, wb0.z), tq[6], va);
+              vc = __ffma2_rn(make_float2(wb1.z, wb1.z), tq[6], vc);
+              sts_pair<T>(row + (unsigned)x * PIX, __fadd2_rn(va, vb));
+              if (x + 1 < row_px) sts_pair<T>(row + (unsigned)(x + 1) * PIX, __fadd2_rn(vc, vd));
+              wa0 = na0; wb0 = nb0; wa1 = na1; wb1 = nb1;
             }
-            bulk_commit();
           }
-          if (n_buf == 1) {                     // a single buffer: its reduction must be read before it is rewritten
-            if (tid == 0) bulk_wait_read<0>();
-            consumer_barrier<NC>();
-          }
+          TICK(5);
+          fence_proxy_async_smem();             // generic-proxy writes -> visible to the bulk engine
+          __syncwarp();
+          if ((tid & 31) == 0) mbar_arrive(&f.row_full[r % kRowBars]);
+          TICK(6);
         }
       }
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(&f.plan_empty[s]);
     }
+#ifdef DGOD_ROI_TIMING
     if (tid == 0) {
-      f.cur_img = g.B;                    // release the zero-fill warp for the remaining images
-      bulk_wait_read<0>();
+      tacc[7] = clock64() - tstart;
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(zero_done) + 256;
+      for (int q = 0; q < 8; ++q) atomicAdd(dst + q, (unsigned long long)tacc[q]);
     }
+#endif
   }
 }
 
