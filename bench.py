@@ -50,6 +50,8 @@ def parse():
     p.add_argument("--domains", type=int, default=0, help="source domains (default 2 at N=1, 3 at N>1)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-fold-bn", action="store_true",
+                   help="keep FrozenBatchNorm2d as separate elementwise passes (default: folded into the conv, utils.py)")
     p.add_argument("--memory-format", default="channels_last", choices=["channels_last", "contiguous"],
                    help="memory format of the detector's convolutions / FPN features")
     return p.parse_args()
@@ -181,6 +183,10 @@ def run_b200(args):
     host = synthetic_batches(4, B, n_dom, 1000 * rank, pin=True)
     resident = [to_device(b, dev) for b in host]
     calibrate(model, resident[0][0])
+    n_folded = 0
+    if not args.no_fold_bn:
+        from dgod_b200.utils import fold_frozen_bn
+        n_folded = fold_frozen_bn(model.detector.backbone)
     if world > 1:
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)
@@ -289,7 +295,10 @@ def run_b200(args):
                    "cache": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no flush needed",
                    "optimizer": f"SGD wd 5e-4 as DGFRCNN.py:98-104, lr {BENCH_LR} (random init diverges at the reference's 2e-3)",
                    "memory_format": args.memory_format,
-                   "backbone_math": "PyTorch defaults (cuDNN conv may use TF32, matmul fp32); hot-path kernels fp32"},
+                   "backbone_math": "PyTorch defaults (cuDNN conv may use TF32, matmul fp32); hot-path kernels fp32",
+                   "frozen_bn": (f"{n_folded} FrozenBatchNorm2d layers evaluated as the epilogue of their conv "
+                                 "(conv(x, w*s) + shift, same function and parameters; dgod_b200/utils.py)") if n_folded
+                   else "separate elementwise passes (torchvision default)"},
         "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roof, "kernels": kernels,
         "loss_finite": bool(torch.isfinite(torch.as_tensor(final_loss)).all()),
     }

@@ -298,3 +298,34 @@ def test_batched_modes_equal_the_reference_per_image_loop(monkeypatch):
                 assert q.grad is None or float(q.grad.abs().max()) == 0.0, n
             else:
                 torch.testing.assert_close(q.grad, p.grad, rtol=1e-4, atol=1e-9, msg=lambda s: f"{n} (mode {mode}): {s}")
+
+
+def test_fold_frozen_bn_is_the_same_function():
+    """utils.fold_frozen_bn: conv + FrozenBatchNorm2d evaluated as one conv — same outputs, same
+    parameter gradients, same state-dict keys (the host-side backbone stays PyTorch/cuDNN)."""
+    import torch
+    from torchvision.models.detection.backbone_utils import resnet_fpn_backbone
+    from dgod_b200.utils import calibrate_frozen_bn, fold_frozen_bn, unfold_frozen_bn
+    torch.manual_seed(0)
+    bb = resnet_fpn_backbone(backbone_name="resnet50", weights=None, trainable_layers=5).double()
+    x = torch.rand(1, 3, 64, 96, dtype=torch.float64)
+    calibrate_frozen_bn(bb, x)
+    keys = list(bb.state_dict().keys())
+
+    def run():
+        bb.zero_grad()
+        out = bb(x)
+        sum(v.square().mean() for v in out.values()).backward()
+        return {k: v.detach().clone() for k, v in out.items()}, bb.body.layer3[0].conv2.weight.grad.clone()
+
+    o0, g0 = run()
+    assert fold_frozen_bn(bb) == 53
+    assert list(bb.state_dict().keys()) == keys
+    o1, g1 = run()
+    for k in o0:
+        torch.testing.assert_close(o1[k], o0[k], rtol=1e-7, atol=1e-9)
+    torch.testing.assert_close(g1, g0, rtol=1e-5, atol=1e-7 * float(g0.abs().max()))   # ReLU inputs within 1e-11 of zero may flip
+    unfold_frozen_bn(bb)
+    o2, _ = run()
+    for k in o0:
+        assert torch.equal(o2[k], o0[k])
