@@ -194,6 +194,24 @@ def batched_nms(boxes: Tensor, scores: Tensor, idxs: Tensor, iou_threshold: floa
 
 
 # --------------------------------------------------------------------------------- Matcher
+def clip_boxes_to_image(boxes: Tensor, size: Tuple[int, int]) -> Tensor:
+    """TV ops/boxes.py:149-182 (same signature).  On the training path the clip is fused into
+    `rpn_proposals` / `detect_candidates`; this stand-alone form serves FCOS eval post-processing
+    (fcos.py:597) and is two clamps on the device."""
+    _need_cuda(boxes)
+    height, width = size
+    x = boxes[..., 0::2].clamp(min=0, max=width)
+    y = boxes[..., 1::2].clamp(min=0, max=height)
+    return torch.stack((x, y), dim=boxes.dim()).reshape(boxes.shape)
+
+
+def remove_small_boxes(boxes: Tensor, min_size: float) -> Tensor:
+    """TV ops/boxes.py:123-146 (same signature): indices of the boxes with both sides >= min_size."""
+    _need_cuda(boxes)
+    ws, hs = boxes[:, 2] - boxes[:, 0], boxes[:, 3] - boxes[:, 1]
+    return torch.where((ws >= min_size) & (hs >= min_size))[0]
+
+
 class Matcher:
     """TV models/detection/_utils.py:313-416, same constructor, attributes and errors."""
 

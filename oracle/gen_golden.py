@@ -9,6 +9,8 @@ Fixtures:
   frcnn_hotpath.npz   fasterrcnn.RegionProposalNetworkWILDS / RoIHeadsWILDS (fasterrcnn.py:90-305) on
                       synthetic FPN features: proposals, anchor labels, sampled RoI labels, pooled
                       features checksum, per-image losses
+  fcos_step.npz       losses + gt_classes of one training forward of fcos.fcos_resnet50_fpn with name-seeded
+                      weights (the dgod_b200.dg_fcos mirror must reproduce them on the GPU)
   frcnn_step.npz      per-image losses of a full fasterrcnn.FastWILDS train step vs the restated
                       oracle.ref_dgfrcnn.RefFasterRCNN with identical weights and RNG
 """
@@ -156,10 +158,57 @@ def gen_step(fasterrcnn):
     print("frcnn_step.npz restated step == reference step bit-for-bit:", {k: v.tolist() for k, v in out["ref"].items()}, missing)
 
 
+# ----------------------------------------------------------------------------------------- FCOS step
+FSTEP = dict(img=(224, 288), batch=3, n_gt=(6, 1, 4), seed=21, min_size=224, max_size=320)
+
+
+def name_seeded_weights(mod: torch.nn.Module, seed: int):
+    """Deterministic weights keyed by parameter NAME (He-scaled), so that the reference model here and
+    the dgod_b200 mirror on the GPU box hold identical parameters without shipping a checkpoint."""
+    g = synth.gen(seed)
+    with torch.no_grad():
+        for _, p in sorted(mod.named_parameters()):
+            if p.dim() > 1:
+                p.copy_(torch.randn(p.shape, generator=g) * (2.0 / p[0].numel()) ** 0.5)
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.01)
+
+
+def fcos_step_inputs():
+    imgs = synth.random_images(FSTEP["batch"], *FSTEP["img"], FSTEP["seed"])
+    targets = []
+    for i, m in enumerate(FSTEP["n_gt"]):
+        g = synth.gen(FSTEP["seed"] * 100 + i)
+        targets.append({"boxes": synth.random_boxes(m, *FSTEP["img"], g, log_size=(2.5, 2.5)),
+                        "labels": torch.randint(1, 9, (m,), generator=g, dtype=torch.int64)})
+    return imgs, targets
+
+
+def gen_fcos_step(fcos):
+    """One training forward of the reference's fcos.fcos_resnet50_fpn (fcos.py:702-788) on CPU: the three
+    losses and the `gt_classes` one-hot it hands to DGFCOS (fcos.py:196-202), incl. a 1-GT image."""
+    model = fcos.fcos_resnet50_fpn(num_classes=9, pretrained_backbone=False, trainable_backbone_layers=3,
+                                   min_size=FSTEP["min_size"], max_size=FSTEP["max_size"])
+    name_seeded_weights(model, 5)
+    model.train()
+    imgs, targets = fcos_step_inputs()
+    out = model(imgs, targets)
+    gtc = out["gt_classes"].detach().numpy()
+    np.savez_compressed(OUT / "fcos_step.npz",
+                        classification=out["classification"].detach().numpy(),
+                        bbox_regression=out["bbox_regression"].detach().numpy(),
+                        bbox_ctrness=out["bbox_ctrness"].detach().numpy(),
+                        gt_classes=np.packbits(gtc.astype(np.uint8), axis=None), gt_shape=np.array(gtc.shape),
+                        param_abs_sum=np.array(sum(float(p.detach().double().abs().sum()) for p in model.parameters())))
+    print("fcos_step.npz", {k: float(out[k]) for k in ("classification", "bbox_regression", "bbox_ctrness")},
+          gtc.shape, int(gtc.sum()))
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     fasterrcnn, fcos = import_reference()
     gen_fcos(fcos)
+    gen_fcos_step(fcos)
     gen_hotpath(fasterrcnn)
     gen_step(fasterrcnn)
 

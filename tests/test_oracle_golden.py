@@ -125,10 +125,11 @@ def test_fixtures_are_current():
         G.OUT = Path(d)
         try:
             G.gen_fcos(fcos)
+            G.gen_fcos_step(fcos)
             G.gen_hotpath(fasterrcnn)
         finally:
             G.OUT = old
-        for name in ("fcos_assign.npz", "frcnn_hotpath.npz"):
+        for name in ("fcos_assign.npz", "fcos_step.npz", "frcnn_hotpath.npz"):
             a, b = np.load(Path(d) / name), np.load(GOLD / name)
             for k in b.files:
                 assert np.array_equal(a[k], b[k]), (name, k)
