@@ -471,33 +471,45 @@ msroi_fwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, int n_ro
   if (n_rows) {
     const unsigned row_bytes = (unsigned)P.row_px * PIX;                // multiple of 128, <= 28 KB
     const int n_stage = min(kStagesMax, RING / (int)row_bytes);        // >= 3
-    if (tid >= NC && tid < NC + n_stage) {
-      // ---------------- producer lanes: lane p owns ring stage p and streams rows p, p + n_stage, ...  (bulk copies
-      // issued by one thread complete one at a time, ~750 cycles each whatever their size —
-      // tools/microbench/bulk_load_issue.cu — while copies of different lanes overlap; one lane per stage also keeps
-      // every mbarrier's phases waited on strictly in order)
+    if (tid >= NC) {
+      // ---------------- producer warp.  Bulk copies issued by one thread complete one at a time, ~750 cycles each
+      // whatever their size (tools/microbench/bulk_load_issue.cu), while copies of different lanes overlap.  Span
+      // mode: lane p owns ring stage p and streams rows p, p + n_stage, ...  Slot mode: lane sx owns sample sx and
+      // issues its 1-2 pixel piece of every row.  Either way every lane waits on the phases of a barrier in order.
+      const int lane = tid - NC;
       const int slot_mode = P.slot_mode, W = g.W[P.level];
       const T* __restrict__ img = reinterpret_cast<const T*>(g.feat[P.level]) + (size_t)P.batch * g.H[P.level] * W * C;
-      unsigned slot_total = 0;
-      if (slot_mode)
-        for (int sx = 0; sx < NS; ++sx)
-          if (P.slot_of[sx] >= 0) slot_total += P.slot_two[sx] ? 2u * PIX : (unsigned)PIX;
-      const T* __restrict__ span0 = img + (size_t)P.x_first * C;
       const unsigned long long keep = policy_evict_last();      // the image's maps are re-read by its other RoIs
-      const int st = tid - NC;
-      for (int i = st; i < n_rows; i += n_stage) {
-        if (i >= n_stage) mbar_wait(&f.empty[st], (unsigned)(i / n_stage - 1) & 1u);
-        const size_t yw = (size_t)P.rows[i] * W;
-        unsigned char* dst = ring + (size_t)st * row_bytes;
-        if (!slot_mode) {
-          mbar_expect_tx(&f.full[st], row_bytes);
-          bulk_load_hint(dst, span0 + yw * C, row_bytes, &f.full[st], keep);
-        } else {
-          mbar_expect_tx(&f.full[st], slot_total);
-          for (int sx = 0; sx < NS; ++sx)
-            if (P.slot_of[sx] >= 0)
-              bulk_load_hint(dst + (size_t)P.slot_of[sx] * 2 * PIX, img + (yw + P.slot_x[sx]) * C,
-                             P.slot_two[sx] ? 2u * PIX : (unsigned)PIX, &f.full[st], keep);
+      if (!slot_mode) {
+        if (lane < n_stage) {
+          const T* __restrict__ span0 = img + (size_t)P.x_first * C;
+          const int st = lane;
+          for (int i = st; i < n_rows; i += n_stage) {
+            if (i >= n_stage) mbar_wait(&f.empty[st], (unsigned)(i / n_stage - 1) & 1u);
+            mbar_expect_tx(&f.full[st], row_bytes);
+            bulk_load_hint(ring + (size_t)st * row_bytes, span0 + (size_t)P.rows[i] * W * C, row_bytes, &f.full[st], keep);
+          }
+        }
+      } else if (lane < NS && P.slot_of[lane] >= 0) {
+        unsigned slot_total = 0;
+        int first = -1;
+        for (int sx = 0; sx < NS; ++sx)
+          if (P.slot_of[sx] >= 0) {
+            slot_total += P.slot_two[sx] ? 2u * PIX : (unsigned)PIX;
+            if (first < 0) first = sx;
+          }
+        const unsigned bytes = P.slot_two[lane] ? 2u * PIX : (unsigned)PIX;
+        const size_t dst_off = (size_t)P.slot_of[lane] * 2 * PIX;
+        const T* __restrict__ src0 = img + (size_t)P.slot_x[lane] * C;
+        int st = 0;
+        unsigned phase = 1u;                 // toggles per lap: lap L >= 1 waits for the (L-1)-th release of its stage
+        for (int i = 0; i < n_rows; ++i) {
+          if (i >= n_stage) mbar_wait(&f.empty[st], phase);
+          // the expected byte count may be posted after some pieces have landed: the phase cannot complete before
+          // this arrival
+          if (lane == first) mbar_expect_tx(&f.full[st], slot_total);
+          bulk_load_hint(ring + (size_t)st * row_bytes + dst_off, src0 + (size_t)P.rows[i] * W * C, bytes, &f.full[st], keep);
+          if (++st == n_stage) { st = 0; phase ^= 1u; }
         }
       }
     } else if (tid < NC) {

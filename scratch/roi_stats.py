@@ -32,3 +32,4 @@ print("pixels per roi mean",(tr*ts).mean(), "span>28:",(ts>28).mean())
 print("levels",np.bincount(lv))
 print("sum rows*span*1KB MB", (tr*ts).sum()*1024/1e6)
 for l in range(2,6): print(l,tr[lv==l].mean(),ts[lv==l].mean())
+for t in (28, 32, 36, 40, 44, 48): print("span >", t, (ts > t).mean(), " share of px:", (tr*ts)[ts > t].sum() / (tr*ts).sum())
