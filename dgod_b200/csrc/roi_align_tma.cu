@@ -10,7 +10,7 @@
 //   msroi_plan_kernel   one warp per RoI: level mapping, sampling taps (the same axis_tap() the
 //                       exact kernels use, i.e. TV's out-of-range skip rule and border clamp), the
 //                       compact list of live feature rows, the separable weight tables.  The result
-//                       is a 4.1 KB "plan" record per RoI in the caller's workspace, so the
+//                       is a 2.4 KB "plan" record per RoI in the caller's workspace, so the
 //                       streaming kernels below do no per-RoI arithmetic at all.
 //   msroi_fwd_tma       one CTA per RoI, warp-specialised.  A producer lane bulk-loads the plan and
 //                       streams the live footprint rows through a ring of up to 8 stages
@@ -146,7 +146,7 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile
 template <int N> __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;\n" ::"n"(N) : "memory"); }
 
 // ---------------------------------------------------------------- the per-RoI plan
-struct alignas(16) ColTap { unsigned off_lo, off_hi, pad0, pad1; float hx, hy, lx, ly; };   // row-buffer byte offsets; (h,h), (l,l)
+struct alignas(16) ColTap { unsigned off_lo, off_hi; float h, l; };   // row-buffer byte offsets of the two taps, their weights
 
 struct alignas(128) RoiPlan {
   // header (64 B)
@@ -156,27 +156,21 @@ struct alignas(128) RoiPlan {
   int level, batch;
   int x_first;           // span mode: first column of the span
   float inv_count;       // 1 / (sr*sr)
-  int sparse_rows;       // backward: every live row puts weight on <= 3 consecutive bins ph (ays)
-  int sparse_cols;       // backward, span mode: every span column puts weight on <= 3 consecutive bins pw (axs, col_start)
-  int pad[6];
+  int pad[8];
   // lists (128 B)
   short rows[kMaxLive];                 // live feature rows, ascending
   short slot_x[kMaxSamp];               // slot mode: first pixel of sample s
   signed char slot_of[kMaxSamp + 2];    // slot mode: compact slot index of a valid sample, -1 otherwise
   unsigned char slot_two[kMaxSamp + 2]; // slot mode: the slot holds two pixels (xhi != xlo)
   unsigned char pad2[12];
-  unsigned char col_start[8];           // span columns [col_start[o], col_start[o+1]) draw on bins pw = o..o+2 (sparse_cols)
-  unsigned char pad3[56];
   // tables
-  ColTap xs[kMaxSamp];                  // 448 B   column taps of every sample
-  float2 ay2[kMaxLive][8];              // 1792 B  (a,a) of the live rows, list order, unscaled
+  ColTap xs[kMaxSamp + 2];              // 256 B   column taps of every sample
+  float ay[kMaxLive][8];                // 896 B   A_y of the live rows, list order, unscaled
   // backward only
-  float4 ays[kMaxLive];                 // 448 B   sparse_rows: (A_y[p0], A_y[p0+1], A_y[p0+2], bits of p0) of live row i
-  float4 axs[kSpanMax + 4];             // 512 B   sparse_cols: the three weights of span column x (+ zero rows: the loop prefetches)
   float ax[kSpanMax + 4][8];            // 1024 B  span mode, dense A_x of the span's columns (+ zero rows)
 };
 static_assert(sizeof(RoiPlan) % 128 == 0, "plans are moved with bulk copies");
-constexpr int kPlanFwdBytes = (int)offsetof(RoiPlan, ays);       // the forward kernel loads this prefix
+constexpr int kPlanFwdBytes = (int)offsetof(RoiPlan, ax);       // the forward kernel loads this prefix
 constexpr int kPlanBwdBytes = (int)sizeof(RoiPlan);
 static_assert(kPlanFwdBytes % 16 == 0, "bulk copy granularity");
 
@@ -294,9 +288,8 @@ msroi_plan_kernel(const RoiDev g, const float* __restrict__ rois, int n_rois, Ro
     P.slot_of[lane] = (signed char)(valid ? t.slot_of[lane] : -1);
     P.slot_two[lane] = (unsigned char)two;
     ColTap e;
-    e.hx = e.hy = in ? t.xh[lane] : 0.f;
-    e.lx = e.ly = in ? t.xl[lane] : 0.f;
-    e.pad0 = e.pad1 = 0u;
+    e.h = in ? t.xh[lane] : 0.f;
+    e.l = in ? t.xl[lane] : 0.f;
     if (!valid) {
       e.off_lo = e.off_hi = 0u;          // weights are zero; offset 0 is always a loaded pixel
     } else if (slot_mode) {
@@ -311,58 +304,9 @@ msroi_plan_kernel(const RoiDev g, const float* __restrict__ rois, int n_rois, Ro
   for (int e = lane; e < kMaxLive * 8; e += 32) {
     const int i = e >> 3, p = e & 7;
     const float a = (i < n_rows && p < kP) ? axis_weight(t.ylo, t.yhi, t.yl, t.yh, t.rows[i], p, sr) : 0.f;
-    P.ay2[i][p] = make_float2(a, a);
+    P.ay[i][p] = a;
   }
   if (!want_ax) return;                // the forward kernel needs nothing below
-  {  // 3-bin windows of the live rows: the separable passes then need 3 instead of 7 multiply-adds
-    bool ok = true;
-    if (lane < n_rows) {
-      int first = kP, last = -1;
-      for (int p = 0; p < kP; ++p)
-        if (axis_weight(t.ylo, t.yhi, t.yl, t.yh, t.rows[lane], p, sr) != 0.f) { first = min(first, p); last = p; }
-      if (last < 0) { first = 0; last = 0; }
-      ok = last - first <= 2;
-      const int p0 = min(first, kP - 3);
-      P.ays[lane] = make_float4(axis_weight(t.ylo, t.yhi, t.yl, t.yh, t.rows[lane], p0, sr),
-                                axis_weight(t.ylo, t.yhi, t.yl, t.yh, t.rows[lane], p0 + 1, sr),
-                                axis_weight(t.ylo, t.yhi, t.yl, t.yh, t.rows[lane], p0 + 2, sr), __int_as_float(p0));
-    }
-    const unsigned all_ok = __all_sync(0xffffffffu, ok);
-    if (lane == 0) P.sparse_rows = all_ok ? 1 : 0;
-  }
-  if (!slot_mode) {  // columns of the span: window starts are non-decreasing in x, so they form 5 contiguous ranges
-    bool ok = true;
-    int w0 = -1;                                   // -1: a gap column inside the span (no weight at all)
-    if (lane < span) {
-      int first = kP, last = -1;
-      for (int p = 0; p < kP; ++p)
-        if (axis_weight(t.xlo, t.xhi, t.xl, t.xh, x_first + lane, p, sr) != 0.f) { first = min(first, p); last = p; }
-      if (last >= 0) {
-        ok = last - first <= 2;
-        w0 = min(first, kP - 3);
-      }
-    }
-    int pm = w0;                                   // inclusive prefix maximum: gap columns inherit a neighbour's window
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int o = __shfl_up_sync(0xffffffffu, pm, d);
-      if (lane >= d) pm = max(pm, o);
-    }
-    ok = ok && (w0 < 0 || w0 == pm);               // window starts must not decrease
-    pm = max(pm, 0);
-    const unsigned all_ok = __all_sync(0xffffffffu, ok);
-    for (int o = 0; o < 8; ++o) {                  // col_start[o] = number of span columns with window start < o
-      const unsigned m = __ballot_sync(0xffffffffu, lane < span && pm < o);
-      if (lane == 0) P.col_start[o] = (unsigned char)(o >= kP - 2 ? span : __popc(m));
-    }
-    if (lane == 0) P.sparse_cols = all_ok ? 1 : 0;
-    P.axs[lane] = lane < span ? make_float4(axis_weight(t.xlo, t.xhi, t.xl, t.xh, x_first + lane, pm, sr),
-                                            axis_weight(t.xlo, t.xhi, t.xl, t.xh, x_first + lane, pm + 1, sr),
-                                            axis_weight(t.xlo, t.xhi, t.xl, t.xh, x_first + lane, pm + 2, sr), 0.f)
-                              : make_float4(0.f, 0.f, 0.f, 0.f);      // kSpanMax + 4 = 32 entries
-  } else if (lane == 0) {
-    P.sparse_cols = 0;
-  }
   if (!slot_mode) {
     for (int e = lane; e < (kSpanMax + 4) * 8; e += 32) {
       const int i = e >> 3, p = e & 7;
@@ -515,6 +459,8 @@ msroi_fwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, int n_ro
     } else if (tid < NC) {
       // ---------------- consumers: thread owns channels 2*tid, 2*tid+1
       const unsigned ring_s = smem_u32(ring) + (unsigned)tid * 2u * (unsigned)sizeof(T);
+      const unsigned xs_s = smem_u32(smem + RING) + (unsigned)offsetof(RoiPlan, xs);
+      const unsigned ay_s = smem_u32(smem + RING) + (unsigned)offsetof(RoiPlan, ay);
       int st = 0;
       unsigned phase = 0u;
       for (int i = 0; i < n_rows; ++i) {
@@ -525,17 +471,16 @@ msroi_fwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, int n_ro
         for (int p = 0; p < kP; ++p) rx[p] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int sx = 0; sx < NS; ++sx) {
-          const uint2 o = *reinterpret_cast<const uint2*>(&P.xs[sx].off_lo);
-          const float4 w = *reinterpret_cast<const float4*>(&P.xs[sx].hx);
-          const float2 v0 = lds_pair<T>(row + o.x), v1 = lds_pair<T>(row + o.y);
-          rx[sx / SR] = __ffma2_rn(make_float2(w.z, w.w), v1, __ffma2_rn(make_float2(w.x, w.y), v0, rx[sx / SR]));
+          const float4 tap = lds_f4(xs_s + sx * 16u);        // off_lo, off_hi (bits), h, l
+          const float2 v0 = lds_pair<T>(row + __float_as_uint(tap.x)), v1 = lds_pair<T>(row + __float_as_uint(tap.y));
+          rx[sx / SR] = __ffma2_rn(make_float2(tap.w, tap.w), v1, __ffma2_rn(make_float2(tap.z, tap.z), v0, rx[sx / SR]));
         }
+        const float4 a03 = lds_f4(ay_s + (unsigned)i * 32u), a46 = lds_f4(ay_s + (unsigned)i * 32u + 16u);
+        const float ay[kP] = {a03.x, a03.y, a03.z, a03.w, a46.x, a46.y, a46.z};
 #pragma unroll
-        for (int ph = 0; ph < kP; ++ph) {
-          const float2 a = P.ay2[i][ph];
+        for (int ph = 0; ph < kP; ++ph)
 #pragma unroll
-          for (int pw = 0; pw < kP; ++pw) acc[ph * kP + pw] = __ffma2_rn(a, rx[pw], acc[ph * kP + pw]);
-        }
+          for (int pw = 0; pw < kP; ++pw) acc[ph * kP + pw] = __ffma2_rn(make_float2(ay[ph], ay[ph]), rx[pw], acc[ph * kP + pw]);
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&f.empty[st]);       // this warp is done with stage st
         if (++st == n_stage) { st = 0; phase ^= 1u; }
@@ -756,11 +701,14 @@ msroi_bwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, const T*
           float2 tq[kP];
 #pragma unroll
           for (int pw = 0; pw < kP; ++pw) tq[pw] = make_float2(0.f, 0.f);
+          {
+            const unsigned ayp = plan_s + (unsigned)s * kPlanBwdBytes + (unsigned)offsetof(RoiPlan, ay) + (unsigned)i * 32u;
+            const float4 a03 = lds_f4(ayp), a46 = lds_f4(ayp + 16u);
+            const float ay[kP] = {a03.x, a03.y, a03.z, a03.w, a46.x, a46.y, a46.z};
 #pragma unroll
-          for (int ph = 0; ph < kP; ++ph) {
-            const float2 a = P.ay2[i][ph];
+            for (int ph = 0; ph < kP; ++ph)
 #pragma unroll
-            for (int pw = 0; pw < kP; ++pw) tq[pw] = __ffma2_rn(a, gr[ph * kP + pw], tq[pw]);
+              for (int pw = 0; pw < kP; ++pw) tq[pw] = __ffma2_rn(make_float2(ay[ph], ay[ph]), gr[ph * kP + pw], tq[pw]);
           }
           TICK(3);
           // ---- the buffer this row goes to must have been read by the bulk engine
@@ -779,7 +727,7 @@ msroi_bwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, const T*
             for (int sx = 0; sx < NS; ++sx) {
               const int slot = P.slot_of[sx];
               if (slot >= 0) {                  // warp-uniform
-                const float h = P.xs[sx].hx, l = P.xs[sx].lx;
+                const float h = P.xs[sx].h, l = P.xs[sx].l;
                 const bool two = P.slot_two[sx];
                 const float w0 = two ? h : h + l;
                 sts_pair<T>(row + (unsigned)(slot * 2) * PIX, __fmul2_rn(make_float2(w0, w0), tq[sx / SR]));

@@ -79,6 +79,7 @@ def run_one(tag, dtype_name="f32", per=512, iters=15):
         t = ws[2048:2048 + 64].view(torch.int64).cpu().tolist()
         names = ["wait plan", "wait G", "gr->regs", "T", "wait buf", "R", "fence+arrive", "total"]
         print("   " + "  ".join(f"{n}={v / 296 / 1965:.1f}us" for n, v in zip(names, t)))
+    VAR.mkdir(parents=True, exist_ok=True)
     torch.save({"out": out.float().cpu(), "g": [g.float().cpu() for g in grads]}, VAR / f"res_{tag}.pt")
     print(f"{tag:14s} {dtype_name} fwd {res['fwd']:7.1f} us  bwd {res['bwd']:7.1f} us", flush=True)
 
