@@ -50,6 +50,8 @@ def parse():
     p.add_argument("--domains", type=int, default=0, help="source domains (default 2 at N=1, 3 at N>1)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-graph-backbone", action="store_true",
+                   help="run the backbone eagerly (default: its forward and backward are captured as CUDA graphs)")
     p.add_argument("--no-fold-bn", action="store_true",
                    help="keep FrozenBatchNorm2d as separate elementwise passes (default: folded into the conv, utils.py)")
     p.add_argument("--memory-format", default="channels_last", choices=["channels_last", "contiguous"],
@@ -190,6 +192,17 @@ def run_b200(args):
     if world > 1:
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)
+    graphed = False
+    if not args.no_graph_backbone:
+        # The ResNet-50-FPN forward and backward are ~4 000 small PyTorch/cuDNN launches per training step with
+        # static shapes (every batch is padded to the same size): capture them as two CUDA graphs.  The hot-path
+        # kernels, the heads and the losses stay eager (data-dependent proposal counts).
+        det = model.detector
+        with torch.no_grad():
+            shape = det.transform([i for i in resident[0][0]], None)[0].tensors.shape
+        sample = torch.rand(shape, device=dev)
+        det.backbone = torch.cuda.make_graphed_callables(det.backbone, (sample,), num_warmup_iters=3)
+        graphed = True
     opt = model.configure_optimizer(lr=BENCH_LR)
     params = [p for p in model.parameters()]
     torch.cuda.synchronize()
@@ -202,16 +215,41 @@ def run_b200(args):
         opt.step()
         return loss
 
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def prefetch(b):
+        """H2D copy of one step's inputs from pinned host memory on the copy stream (as a DataLoader with
+        pin_memory + non_blocking does); the returned event orders it before the step that uses it."""
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(copy_stream):
+            d = to_device(b, dev)
+            for t in (*d[0], *d[1], *d[2], d[3]):
+                t.record_stream(main)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return d, ev
+
     def cycle(from_host: bool):
-        last = None
+        if not from_host:
+            last = None
+            for s in range(len(CYCLE)):
+                last = train_step(resident[(s // 2) % 4])
+            return last
+        # end to end: every step's inputs come from the host and every step's loss goes back to it.  The copy
+        # of step s+1 overlaps the compute of step s, and the loss of step s is read while step s+1 is queued
+        # (the host stays one step ahead instead of draining the GPU after every step).
+        nxt = prefetch(host[0])
+        pending = None
         for s in range(len(CYCLE)):
-            b = host[(s // 2) % 4] if from_host else resident[(s // 2) % 4]
-            if from_host:
-                b = to_device(b, dev)
-            last = train_step(b)
-            if from_host:
-                last = last.item()          # D2H read of the step's result
-        return last
+            cur, ev = nxt
+            torch.cuda.current_stream().wait_event(ev)
+            if s + 1 < len(CYCLE):
+                nxt = prefetch(host[((s + 1) // 2) % 4])
+            loss = train_step(cur)
+            if pending is not None:
+                pending.item()              # D2H read of the previous step's result
+            pending = loss
+        return pending.item()
 
     def barrier():
         if world > 1:
@@ -298,7 +336,9 @@ def run_b200(args):
                    "backbone_math": "PyTorch defaults (cuDNN conv may use TF32, matmul fp32); hot-path kernels fp32",
                    "frozen_bn": (f"{n_folded} FrozenBatchNorm2d layers evaluated as the epilogue of their conv "
                                  "(conv(x, w*s) + shift, same function and parameters; dgod_b200/utils.py)") if n_folded
-                   else "separate elementwise passes (torchvision default)"},
+                   else "separate elementwise passes (torchvision default)",
+                   "backbone_launch": "forward and backward captured as CUDA graphs (torch.cuda.make_graphed_callables)"
+                   if graphed else "eager"},
         "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roof, "kernels": kernels,
         "loss_finite": bool(torch.isfinite(torch.as_tensor(final_loss)).all()),
     }
