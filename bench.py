@@ -238,6 +238,11 @@ def run_b200(args):
         # end to end: every step's inputs come from the host and every step's loss goes back to it.  The copy
         # of step s+1 overlaps the compute of step s, and the loss of step s is read while step s+1 is queued
         # (the host stays one step ahead instead of draining the GPU after every step).
+        if os.environ.get("DGOD_E2E_SIMPLE"):       # copy, step, read back, strictly in sequence
+            last = None
+            for s in range(len(CYCLE)):
+                last = train_step(to_device(host[(s // 2) % 4], dev)).item()
+            return last
         nxt = prefetch(host[0])
         pending = None
         for s in range(len(CYCLE)):
