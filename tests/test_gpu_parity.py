@@ -318,6 +318,39 @@ def test_multiscale_roi_align_tma_paths(dtype, tol, with_offsets):
     np.testing.assert_allclose(tot, sum(float(g.astype(np.float64).sum()) for g in grads), rtol=5e-3 if dtype == torch.bfloat16 else 1e-4)
 
 
+@pytest.mark.parametrize("C,sr", [(64, 2), (128, 2), (256, 1)])
+def test_multiscale_roi_align_tma_other_instantiations(C, sr):
+    """The other instantiated shapes of the TMA kernels (1 or 2 consumer warps, sampling_ratio 1), a single
+    RoI, and zero RoIs (the backward must still overwrite the gradient maps with zeros)."""
+    from dgod_b200 import ops
+    img_h, img_w, B = 200, 264, 2
+    feats = synth.random_features(B, C, img_h, img_w, seed=31)
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+    for n in (150, 1, 0):
+        boxes = [_boxes(n, 40 + i, img_h, img_w) for i in range(B)]
+        rois = synth.rois_from_boxes(boxes).reshape(-1, 5)
+        xs = [f.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for f in feats]
+        got = ops.multiscale_roi_align(xs, rois.to(DEV), scales, 7, sr, 2, 5)
+        assert got.shape == (rois.shape[0], C, 7, 7)
+        go = torch.randn(got.shape, generator=synth.gen(32))
+        ops.BACKWARD_ALGO = 3
+        try:
+            for t in xs:
+                t.grad = torch.full_like(t, 7.0).contiguous(memory_format=torch.channels_last)   # must not leak through
+                t.grad = None
+            got.backward(go.to(DEV))
+        finally:
+            ops.BACKWARD_ALGO = 0
+        if n == 0:
+            assert all(float(x.grad.abs().max()) == 0.0 for x in xs)
+            continue
+        ref = O.msroi_align_fwd([f.numpy() for f in feats], rois.numpy(), scales, 7, 7, sr, 2, 5)
+        np.testing.assert_allclose(got.detach().cpu().numpy(), ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+        grads = O.msroi_align_bwd(go.numpy(), [tuple(f.shape) for f in feats], rois.numpy(), scales, sr, 2, 5)
+        for x, gr in zip(xs, grads):
+            np.testing.assert_allclose(x.grad.cpu().numpy(), gr, rtol=1e-5, atol=1e-5 * max(np.abs(gr).max(), 1e-3))
+
+
 def test_roi_align_empty_and_errors():
     ops = _ops()
     x = torch.randn(1, 8, 16, 16, device=DEV)

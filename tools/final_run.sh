@@ -1,3 +1,4 @@
+# Round-end measurement batch run under gpurun: tests, smoke, both bench arms, op sweep, ncu captures -> gpurun_out/s30_*
 set -x
 python -m pytest tests/ -m gpu -x -q > gpurun_out/s30_pytest.log 2>&1; tail -3 gpurun_out/s30_pytest.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/s30_smoke.log 2>&1; tail -1 gpurun_out/s30_smoke.log

@@ -15,6 +15,12 @@ B = 8
 model = DGFRCNN(9, B, "dg", bench.REG_WEIGHTS, 2).to(dev).train().to(memory_format=torch.channels_last)
 res = [bench.to_device(b, dev) for b in bench.synthetic_batches(4, B, 2, 0)]
 bench.calibrate(model, res[0][0])
+if "--eager" not in sys.argv:          # bench.py's default host-side setup: folded frozen BN + graphed backbone
+    from dgod_b200.utils import fold_frozen_bn
+    fold_frozen_bn(model.detector.backbone)
+    with torch.no_grad():
+        shape = model.detector.transform([i for i in res[0][0]], None)[0].tensors.shape
+    model.detector.backbone = torch.cuda.make_graphed_callables(model.detector.backbone, (torch.rand(shape, device=dev),), num_warmup_iters=3)
 opt = model.configure_optimizer(lr=bench.BENCH_LR)
 
 def step(b):
@@ -31,9 +37,17 @@ for s in range(8):
     mode = model.mode
     t0 = time.perf_counter(); step(res[(s // 2) % 4]); torch.cuda.synchronize()
     print(f"mode {mode}: {1e3 * (time.perf_counter() - t0):7.1f} ms")
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for s in range(8):
+    step(res[(s // 2) % 4])
+torch.cuda.synchronize()
+print(f"8-step cycle, no syncs in between: {1e3 * (time.perf_counter() - t0):7.1f} ms")
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for s in range(8):
         step(res[(s // 2) % 4])
     torch.cuda.synchronize()
+ka = prof.key_averages()
+gpu_ms = sum(e.self_device_time_total for e in ka) / 1e3
+print(f"sum of kernel time over the 8-step cycle: {gpu_ms:.1f} ms")
 print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=40, max_name_column_width=70))
