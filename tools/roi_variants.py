@@ -1,13 +1,13 @@
 """Experiment harness: build variants of roi_align_tma.cu with extra -D flags (CPU box), time them on the GPU.
 
-  python scratch/variants.py build tagA:-DX=1,-DY tagB:...     -> scratch/var/lib_<tag>.so
-  python scratch/variants.py run [tags...]                     -> kernel_us of fwd/bwd per variant + max rel err vs 'base'
+  python tools/roi_variants.py build tagA:-DX=1,-DY tagB:...     -> tools/_variants/lib_<tag>.so
+  python tools/roi_variants.py run [tags...]                     -> kernel_us of fwd/bwd per variant + max rel err vs 'base'
 """
 import sys, subprocess, os, ctypes as C, statistics
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-VAR = ROOT / "scratch" / "var"
+VAR = ROOT / "tools" / "_variants"
 
 def build(specs):
     from dgod_b200 import build as B
