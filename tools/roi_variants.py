@@ -63,7 +63,7 @@ def run_one(tag, dtype_name="f32", per=512, iters=15):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     st = ops._stream()
     def fwd(): ops.check(lib.dgod_msroi_align_fwd(C.byref(cfg), fptrs, ops._p(rois), K, ops._p(out), ops._p(ws), wsb, st))
-    def bwd(): ops.check(lib.dgod_msroi_align_bwd(C.byref(cfg), ops._p(go), ops._p(rois), K, None, gptrs, 3, ops._p(ws), wsb, st))
+    def bwd(): ops.check(lib.dgod_msroi_align_bwd(C.byref(cfg), ops._p(go), ops._p(rois), K, None, gptrs, int(os.environ.get('BWD_ALGO', 3)), ops._p(ws), wsb, st))
     res = {}
     for name, fn in (("fwd", fwd), ("bwd", bwd)):
         for _ in range(3): fn()
