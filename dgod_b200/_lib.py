@@ -57,6 +57,9 @@ SIGNATURES = {
     "dgod_iou_match": (i32, [vp, vp, vp, i32, i32, vp, vp, i32, i32, f64, f64, i32,
                              vp, vp, vp, vp, vp, vp, sz, vp]),
     "dgod_fcos_assign": (i32, [vp, i32, i32, i32, f64, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp]),
+    "dgod_fcos_loss_workspace_bytes": (sz, [C.c_longlong]),
+    "dgod_fcos_loss_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, sz, vp]),
+    "dgod_fcos_loss_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp]),
     "dgod_nms_workspace_bytes": (sz, [i32, i32, i32]),
     "dgod_nms_batched": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, f64, i32, i32, vp, vp, vp, vp, sz, vp]),
     "dgod_rpn_workspace_bytes": (sz, [C.POINTER(RpnConfig)]),

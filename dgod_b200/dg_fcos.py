@@ -33,9 +33,18 @@ from . import ops
 
 # --------------------------------------------------------------------------------- detector
 class FCOSHead(_TVFCOSHead):
-    """fcos.py:103-213.  `compute_loss` takes the targets the assignment kernel already gathered."""
+    """fcos.py:103-213.  `compute_loss` takes the targets the assignment kernel already gathered and, by
+    default, evaluates the focal / GIoU / centre-ness tail (fcos.py:149-202) with the fused `ops.fcos_loss`
+    kernels (forward 2 launches, backward 1, no host sync); `fused_loss = False` keeps the ATen chain."""
+
+    fused_loss = True
 
     def compute_loss(self, targets, head_outputs: Dict[str, Tensor], anchors: List[Tensor], assigned) -> Dict[str, Tensor]:
+        if self.fused_loss:
+            _, cls_t, box_t, onehot = assigned
+            out = ops.fcos_loss(head_outputs["cls_logits"], head_outputs["bbox_regression"], head_outputs["bbox_ctrness"],
+                                anchors[0], cls_t, box_t)
+            return {"classification": out[0], "bbox_regression": out[1], "bbox_ctrness": out[2], "gt_classes": onehot}
         cls_logits = head_outputs["cls_logits"]            # [B, N, C]
         bbox_regression = head_outputs["bbox_regression"]  # [B, N, 4]
         bbox_ctrness = head_outputs["bbox_ctrness"]        # [B, N, 1]

@@ -380,6 +380,79 @@ def fcos_assign(anchors: Tensor, gt_boxes: Sequence[Tensor], num_anchors_per_lev
     return idx
 
 
+@torch.library.custom_op("dgod_b200::fcos_loss", mutates_args=())
+def _fcos_loss_op(cls_logits: Tensor, bbox_regression: Tensor, bbox_ctrness: Tensor, anchors: Tensor,
+                  cls_targets: Tensor, box_targets: Tensor, alpha: float) -> Tensor:
+    _need_cuda(cls_logits, bbox_regression, bbox_ctrness, anchors, cls_targets, box_targets)
+    lib = _lib.load()
+    B, N, Cn = cls_logits.shape
+    out = torch.empty(4, dtype=torch.float32, device=cls_logits.device)
+    wsb = lib.dgod_fcos_loss_workspace_bytes(B * N)
+    ws = _ws(wsb, cls_logits.device)
+    tok = KernelTimer.start("fcos_loss_fwd", B * N * (4 * (Cn + 5) + 8 + 16) + 16 * N)
+    check(lib.dgod_fcos_loss_fwd(_p(cls_logits), _p(bbox_regression), _p(bbox_ctrness), _p(anchors), _p(cls_targets),
+                                 _p(box_targets), B, N, Cn, float(alpha), _p(out), _p(ws), wsb, _stream()))
+    KernelTimer.stop(tok)
+    return out
+
+
+@_fcos_loss_op.register_fake
+def _(cls_logits, bbox_regression, bbox_ctrness, anchors, cls_targets, box_targets, alpha):
+    return cls_logits.new_empty((4,), dtype=torch.float32)
+
+
+@torch.library.custom_op("dgod_b200::fcos_loss_backward", mutates_args=())
+def _fcos_loss_bwd_op(cls_logits: Tensor, bbox_regression: Tensor, bbox_ctrness: Tensor, anchors: Tensor,
+                      cls_targets: Tensor, box_targets: Tensor, alpha: float, losses: Tensor,
+                      grad_losses: Tensor) -> List[Tensor]:
+    _need_cuda(cls_logits, losses, grad_losses)
+    lib = _lib.load()
+    B, N, Cn = cls_logits.shape
+    g_cls, g_reg, g_ctr = torch.empty_like(cls_logits), torch.empty_like(bbox_regression), torch.empty_like(bbox_ctrness)
+    tok = KernelTimer.start("fcos_loss_bwd", 2 * B * N * 4 * (Cn + 5) + B * N * (8 + 16) + 16 * N)
+    check(lib.dgod_fcos_loss_bwd(_p(cls_logits), _p(bbox_regression), _p(bbox_ctrness), _p(anchors), _p(cls_targets),
+                                 _p(box_targets), B, N, Cn, float(alpha), _p(losses), _p(grad_losses), _p(g_cls),
+                                 _p(g_reg), _p(g_ctr), _stream()))
+    KernelTimer.stop(tok)
+    return [g_cls, g_reg, g_ctr]
+
+
+@_fcos_loss_bwd_op.register_fake
+def _(cls_logits, bbox_regression, bbox_ctrness, anchors, cls_targets, box_targets, alpha, losses, grad_losses):
+    return [torch.empty_like(cls_logits), torch.empty_like(bbox_regression), torch.empty_like(bbox_ctrness)]
+
+
+def _fcos_loss_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs[:6], output)
+    ctx.alpha = inputs[6]
+
+
+def _fcos_loss_backward(ctx, grad):
+    cls_logits, reg, ctr, anchors, ct, bt, losses = ctx.saved_tensors
+    g = _fcos_loss_bwd_op(cls_logits, reg, ctr, anchors, ct, bt, ctx.alpha, losses, grad[:3].contiguous().float())
+    return g[0], g[1], g[2], None, None, None, None
+
+
+_fcos_loss_op.register_autograd(_fcos_loss_backward, setup_context=_fcos_loss_setup)
+
+
+def fcos_loss(cls_logits: Tensor, bbox_regression: Tensor, bbox_ctrness: Tensor, anchors: Tensor,
+              cls_targets: Tensor, box_targets: Tensor, alpha: float = 0.25) -> Tensor:
+    """fcos.py:149-202 fused: returns a device tensor [4] = classification, bbox_regression, bbox_ctrness
+    (each already divided by max(1, #foreground)) and #foreground — differentiable w.r.t. the three head
+    outputs, no host sync.  cls_logits [B,N,C], bbox_regression [B,N,4], bbox_ctrness [B,N,1] fp32;
+    anchors [N,4]; cls_targets [B,N] int64 (-1 = background) and box_targets [B,N,4] from `fcos_assign`."""
+    for t in (cls_logits, bbox_regression, bbox_ctrness):
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"fcos_loss: float32 head outputs expected, got {t.dtype}")
+    B, N, _ = cls_logits.shape
+    if bbox_regression.shape != (B, N, 4) or bbox_ctrness.numel() != B * N or cls_targets.shape != (B, N):
+        raise RuntimeError("fcos_loss: expected cls_logits [B,N,C], bbox_regression [B,N,4], bbox_ctrness [B,N,1], "
+                           "cls_targets [B,N]")
+    return _fcos_loss_op(cls_logits.contiguous(), bbox_regression.contiguous(), bbox_ctrness.contiguous(),
+                         _f32c(anchors), cls_targets.contiguous(), _f32c(box_targets), float(alpha))
+
+
 # --------------------------------------------------------------------------------- RoIAlign
 def _roi_config(feats: Sequence[Tensor], scales: Sequence[float], ph: int, pw: int, sr: int, aligned: bool,
                 k_min: int, k_max: int, s0: float, lvl0: float, eps: float = 1e-6):

@@ -15,6 +15,7 @@
  *   dgod_matcher            TV models/detection/_utils.py:357-416
  *   dgod_iou_match          TV rpn.py:193-229 and TV roi_heads.py:580-613 (fasterrcnn.py:187,272)
  *   dgod_fcos_assign        fcos.py:510-548 and fcos.py:136-158
+ *   dgod_fcos_loss_fwd/_bwd fcos.py:149-202 (focal + GIoU + centre-ness losses of FCOSHead.compute_loss)
  *   dgod_nms_batched        TV ops/boxes.py:20-120 -> torchvision::nms (TV rpn.py:289,
  *                           TV roi_heads.py:728, fcos.py:608)
  *   dgod_rpn_proposals      fasterrcnn.py:174-182 -> TV _utils.py:162-224, TV rpn.py:231-297,
@@ -115,6 +116,27 @@ int dgod_fcos_assign(const float* anchors /*device [n_anchors,4]*/, int n_anchor
                      const int32_t* gt_offsets /*device [n_img+1]*/, int n_img,
                      int64_t* matched_idx, int64_t* cls_targets, float* box_targets,
                      float* onehot, int num_classes, dgod_stream_t stream);
+
+/* FCOS loss tail: fcos.py:149-202 after the target gather — sigmoid focal loss
+ * (alpha, gamma 2) over [n_img, n_anchors, num_classes] logits with one_hot(cls_targets), GIoU loss of
+ * the decoded boxes (BoxLinearCoder, normalize_by_size) and BCE of the centre-ness logit against
+ * sqrt(min(l,r)/max(l,r) * min(t,b)/max(t,b)) over the foreground (cls_targets >= 0), each divided by
+ * max(1, #foreground).  losses: device fp32 [4] = classification, bbox_regression, bbox_ctrness,
+ * #foreground (no host sync).  All tensors fp32 contiguous, box tensors 16-byte aligned; cls_targets /
+ * box_targets are what dgod_fcos_assign writes.  The backward takes d(total)/d(losses[0..2]) as a
+ * device fp32 [3] and writes dense gradients of the three head outputs (zeros on the background). */
+size_t dgod_fcos_loss_workspace_bytes(long long n_locations);
+int dgod_fcos_loss_fwd(const float* cls_logits, const float* bbox_regression, const float* bbox_ctrness,
+                       const float* anchors /*device [n_anchors,4]*/, const int64_t* cls_targets,
+                       const float* box_targets, int n_img, int n_anchors, int num_classes, float alpha,
+                       float* losses /*device [4]*/, void* workspace, size_t workspace_bytes,
+                       dgod_stream_t stream);
+int dgod_fcos_loss_bwd(const float* cls_logits, const float* bbox_regression, const float* bbox_ctrness,
+                       const float* anchors, const int64_t* cls_targets, const float* box_targets,
+                       int n_img, int n_anchors, int num_classes, float alpha,
+                       const float* losses /*device [4] from the forward*/,
+                       const float* grad_losses /*device [3]*/, float* grad_cls_logits,
+                       float* grad_bbox_regression, float* grad_bbox_ctrness, dgod_stream_t stream);
 
 /* ------------------------------------------------------------------ batched NMS */
 

@@ -130,6 +130,17 @@ def fcos_assign(anchors, n_first, n_last, gt, gt_labels, radius=1.5):
     return idx, cls, bt
 
 
+def fcos_loss(cls_logits, bbox_regression, bbox_ctrness, anchors, cls_targets, box_targets, alpha=0.25):
+    """fcos.py:149-202 -> float32 [4]: classification, bbox_regression, bbox_ctrness, #foreground."""
+    cl, rg, ct = _f32(cls_logits), _f32(bbox_regression), _f32(bbox_ctrness).reshape(-1)
+    B, N, Cn = cl.shape
+    an, tg, bt = _f32(anchors).reshape(-1, 4), _i64(cls_targets).reshape(-1), _f32(box_targets).reshape(-1, 4)
+    out = np.empty(4, np.float32)
+    lib().o_fcos_loss(_p(cl), _p(rg), _p(ct), _p(an), _p(tg), _p(bt), C.c_int(B), C.c_int(N), C.c_int(Cn),
+                      C.c_float(alpha), _p(out))
+    return out
+
+
 # ---------------------------------------------------------------------------------- RoIAlign
 def roi_align_fwd(x, rois, scale, ph, pw, sr, aligned=False):
     """torchvision::roi_align CPU forward (TV ops/roi_align.py:204-260)."""

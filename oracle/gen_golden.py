@@ -9,6 +9,7 @@ Fixtures:
   frcnn_hotpath.npz   fasterrcnn.RegionProposalNetworkWILDS / RoIHeadsWILDS (fasterrcnn.py:90-305) on
                       synthetic FPN features: proposals, anchor labels, sampled RoI labels, pooled
                       features checksum, per-image losses
+  fcos_loss.npz       fcos.FCOSHead.compute_loss (fcos.py:124-202) on seeded head outputs: losses and gradients
   fcos_step.npz       losses + gt_classes of one training forward of fcos.fcos_resnet50_fpn with name-seeded
                       weights (the dgod_b200.dg_fcos mirror must reproduce them on the GPU)
   frcnn_step.npz      per-image losses of a full fasterrcnn.FastWILDS train step vs the restated
@@ -81,6 +82,38 @@ def gen_fcos(fcos):
     np.savez_compressed(OUT / "fcos_assign.npz", matched=torch.stack(matched).numpy(),
                         gt_classes=loss["gt_classes"].numpy().astype(np.uint8))
     print("fcos_assign.npz", torch.stack(matched).shape, int((torch.stack(matched) >= 0).sum()), "matched")
+
+
+def fcos_loss_inputs():
+    """Seeded head outputs for the inputs of fcos_inputs(): logits ~ N(0, 2), regression in (0.05, 2.05) (the head
+    ends in ReLU, fcos.py:299), centre-ness logits ~ N(0, 1)."""
+    anchors, npl, gts, labels = fcos_inputs()
+    B, N = len(gts), len(anchors)
+    g = synth.gen(4242)
+    return {"cls_logits": torch.randn(B, N, 9, generator=g) * 2.0,
+            "bbox_regression": torch.rand(B, N, 4, generator=g) * 2.0 + 0.05,
+            "bbox_ctrness": torch.randn(B, N, 1, generator=g)}
+
+
+def gen_fcos_loss(fcos):
+    """fcos.FCOSHead.compute_loss (fcos.py:124-202) on seeded head outputs: the three losses and their gradients."""
+    anchors, npl, gts, labels = fcos_inputs()
+    B = len(gts)
+    a = torch.from_numpy(anchors)
+    targets = [{"boxes": g, "labels": l} for g, l in zip(gts, labels)]
+    stub = types.SimpleNamespace(center_sampling_radius=1.5,
+                                 head=types.SimpleNamespace(compute_loss=lambda t, h, an, m: m))
+    matched = fcos.FCOS.compute_loss(stub, targets, None, [a] * B, npl)
+    head = types.SimpleNamespace(box_coder=fcos.BoxLinearCoder(normalize_by_size=True))
+    ho = {k: v.requires_grad_(True) for k, v in fcos_loss_inputs().items()}
+    loss = fcos.FCOSHead.compute_loss(head, targets, ho, [a] * B, [m.clone() for m in matched])
+    total = loss["classification"] + 2.0 * loss["bbox_regression"] + 3.0 * loss["bbox_ctrness"]
+    total.backward()
+    np.savez_compressed(OUT / "fcos_loss.npz",
+                        losses=np.array([float(loss[k]) for k in ("classification", "bbox_regression", "bbox_ctrness")], np.float32),
+                        grad_cls=ho["cls_logits"].grad.numpy(), grad_reg=ho["bbox_regression"].grad.numpy(),
+                        grad_ctr=ho["bbox_ctrness"].grad.numpy())
+    print("fcos_loss.npz", {k: float(loss[k]) for k in ("classification", "bbox_regression", "bbox_ctrness")})
 
 
 # ----------------------------------------------------------------------------------------- Faster R-CNN hot path
@@ -208,6 +241,7 @@ def main():
     OUT.mkdir(parents=True, exist_ok=True)
     fasterrcnn, fcos = import_reference()
     gen_fcos(fcos)
+    gen_fcos_loss(fcos)
     gen_fcos_step(fcos)
     gen_hotpath(fasterrcnn)
     gen_step(fasterrcnn)

@@ -107,6 +107,12 @@ def test_fcos_training_forward_matches_reference_golden(exact_convs):
     assert not want[1, :, 1:].any()                                           # the 1-GT image: all-zero labels (fcos.py:139)
     for k in ("classification", "bbox_regression", "bbox_ctrness"):
         np.testing.assert_allclose(float(out[k]), float(gold[k]), rtol=2e-4)
+    # the fused loss tail and the ATen chain of fcos.py:149-202 agree on the same head outputs
+    model.head.fused_loss = False
+    out2 = model([i.cuda() for i in imgs], [{k: v.cuda() for k, v in t.items()} for t in targets])
+    model.head.fused_loss = True
+    for k in ("classification", "bbox_regression", "bbox_ctrness"):
+        np.testing.assert_allclose(float(out[k]), float(out2[k]), rtol=1e-5)
     # and the eval path: detections come out of the NMS kernel with TV's layout
     model.eval()
     with torch.no_grad():

@@ -488,3 +488,36 @@ def test_grl_linear_matches_unfused():
     assert torch.equal(y1, y2)
     torch.testing.assert_close(g1, x.grad, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(gw1, lin.weight.grad, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------- FCOS loss tail
+def test_fcos_loss_tail_forward_backward():
+    """ops.fcos_loss (fcos.py:149-202 fused) against the golden losses AND gradients produced by the reference's
+    own FCOSHead.compute_loss + autograd on CPU (oracle/gen_golden.py::gen_fcos_loss), and against the C oracle."""
+    from pathlib import Path
+    from oracle import gen_golden as G
+    ops = _ops()
+    gold = np.load(Path(__file__).parent / "golden" / "fcos_loss.npz")
+    anchors, npl, gts, labels = G.fcos_inputs()
+    ho = {k: v.to(DEV).requires_grad_(True) for k, v in G.fcos_loss_inputs().items()}
+    a = torch.from_numpy(anchors).to(DEV)
+    idx, cls_t, box_t, onehot = ops.fcos_assign(a, [g.to(DEV) for g in gts], npl, 1.5,
+                                                gt_labels=[l.to(DEV) for l in labels], num_classes=9)
+    out = ops.fcos_loss(ho["cls_logits"], ho["bbox_regression"], ho["bbox_ctrness"], a, cls_t, box_t)
+    ref = O.fcos_loss(ho["cls_logits"].detach().cpu().numpy(), ho["bbox_regression"].detach().cpu().numpy(),
+                      ho["bbox_ctrness"].detach().cpu().numpy(), anchors, cls_t.cpu().numpy(), box_t.cpu().numpy())
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref, rtol=1e-5)
+    np.testing.assert_allclose(out[:3].detach().cpu().numpy(), gold["losses"], rtol=1e-5)
+    assert float(out[3]) == float((cls_t >= 0).sum())
+    (out[0] + 2.0 * out[1] + 3.0 * out[2]).backward()
+    for name, key in (("cls_logits", "grad_cls"), ("bbox_regression", "grad_reg"), ("bbox_ctrness", "grad_ctr")):
+        g, want = ho[name].grad.cpu().numpy(), gold[key]
+        np.testing.assert_allclose(g, want, rtol=1e-4, atol=1e-5 * np.abs(want).max())
+    # background locations get exactly zero regression / centre-ness gradient
+    bg = (cls_t < 0).cpu().numpy()
+    assert not ho["bbox_regression"].grad.cpu().numpy()[bg].any() and not ho["bbox_ctrness"].grad.cpu().numpy()[bg].any()
+    # no foreground at all: the three losses are finite and divided by 1 (fcos.py:197-200)
+    none = torch.full_like(cls_t, -1)
+    z = ops.fcos_loss(ho["cls_logits"].detach(), ho["bbox_regression"].detach(), ho["bbox_ctrness"].detach(), a, none, box_t)
+    assert float(z[3]) == 0.0 and float(z[1]) == 0.0 and float(z[2]) == 0.0 and np.isfinite(float(z[0]))
+

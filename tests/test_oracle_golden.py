@@ -27,6 +27,21 @@ def test_fcos_assignment_and_targets_match_reference():
     assert (gold["matched"][2] >= 0).any() and not gold["gt_classes"][2][:, 1:].any()   # the `<= 1` quirk
 
 
+def test_fcos_loss_tail_matches_reference():
+    """oracle o_fcos_loss == fcos.FCOSHead.compute_loss of the reference (fcos.py:149-202) on seeded head outputs."""
+    gold = np.load(GOLD / "fcos_loss.npz")
+    anchors, npl, gts, labels = G.fcos_inputs()
+    ho = G.fcos_loss_inputs()
+    cls_t, box_t = [], []
+    for g, l in zip(gts, labels):
+        _, c, b = O.fcos_assign(anchors, npl[0], npl[-1], g.numpy(), l.numpy(), 1.5)
+        cls_t.append(c), box_t.append(b)
+    out = O.fcos_loss(ho["cls_logits"].numpy(), ho["bbox_regression"].numpy(), ho["bbox_ctrness"].numpy(), anchors,
+                      np.stack(cls_t), np.stack(box_t))
+    np.testing.assert_allclose(out[:3], gold["losses"], rtol=1e-5)
+    assert out[3] == sum(int((c >= 0).sum()) for c in cls_t) > 0
+
+
 class _Prefixed(nn.Module):
     """Gives sub-modules the attribute names they have inside the reference's containers so that
     gen_golden.seeded_module_weights draws identical weights."""
@@ -126,10 +141,11 @@ def test_fixtures_are_current():
         try:
             G.gen_fcos(fcos)
             G.gen_fcos_step(fcos)
+            G.gen_fcos_loss(fcos)
             G.gen_hotpath(fasterrcnn)
         finally:
             G.OUT = old
-        for name in ("fcos_assign.npz", "fcos_step.npz", "frcnn_hotpath.npz"):
+        for name in ("fcos_assign.npz", "fcos_step.npz", "fcos_loss.npz", "frcnn_hotpath.npz"):
             a, b = np.load(Path(d) / name), np.load(GOLD / name)
             for k in b.files:
                 assert np.array_equal(a[k], b[k]), (name, k)

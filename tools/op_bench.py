@@ -190,6 +190,28 @@ def bench_fcos(args, out):
         out.append(row("fcos_assign", f"B8 {n} locations x 20 GT", us, 8 * (16 * n + 16 * 20 + 8 * n)))
         us = time_op(lambda: ops.fcos_assign(a, gts, npl, 1.5, gt_labels=labels, num_classes=9), args.iters)
         out.append(row("fcos_assign+targets", f"B8 {n} locations x 20 GT", us, 8 * (16 * n + 16 * 20 + 8 * n + 8 * n + 16 * n + 36 * n)))
+        # loss tail (fcos.py:149-202): fused kernels vs the reference's ATen chain on the same device
+        from dgod_b200.dg_fcos import FCOSHead
+        g = synth.gen(77)
+        ho = {"cls_logits": (torch.randn(8, n, 9, generator=g) * 2).to(DEV).requires_grad_(True),
+              "bbox_regression": (torch.rand(8, n, 4, generator=g) * 2 + 0.05).to(DEV).requires_grad_(True),
+              "bbox_ctrness": torch.randn(8, n, 1, generator=g).to(DEV).requires_grad_(True)}
+        assigned = ops.fcos_assign(a, gts, npl, 1.5, gt_labels=labels, num_classes=9)
+        head = FCOSHead(256, 1, 9).to(DEV)
+        alg = 8 * n * (4 * 14 + 8 + 16) + 16 * n
+
+        def step(fused):
+            head.fused_loss = fused
+            for t in ho.values():
+                t.grad = None
+            d = head.compute_loss(None, ho, [a] * 8, assigned)
+            (d["classification"] + d["bbox_regression"] + d["bbox_ctrness"]).backward()
+
+        us = time_op(lambda: step(True), args.iters)
+        out.append(row("fcos_loss fwd+bwd (fused)", f"B8 {n} locations", us, 3 * alg))
+        if args.tv:
+            t = time_op(lambda: step(False), args.iters)
+            out.append(row("torchvision_ops_fcos_loss fwd+bwd (ATen chain of fcos.py:149-202)", f"B8 {n} locations", t, 3 * alg))
 
 
 def bench_rpn(args, out):
