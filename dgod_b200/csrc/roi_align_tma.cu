@@ -12,22 +12,25 @@
 //                       compact list of live feature rows, the separable weight tables.  The result
 //                       is a 2.4 KB "plan" record per RoI in the caller's workspace, so the
 //                       streaming kernels below do no per-RoI arithmetic at all.
-//   msroi_fwd_tma       one CTA per RoI, warp-specialised.  A producer lane bulk-loads the plan and
-//                       streams the live footprint rows through a ring of up to 8 stages
-//                       (cp.async.bulk global->shared, mbarrier complete_tx).  C/2 consumer threads
-//                       own two adjacent channels each (packed fp32 FFMA2), keep the 49 pooled
-//                       values of both in registers and hand stages back through per-stage
+//   msroi_fwd_tma       one CTA per RoI, warp-specialised.  Thread 0 bulk-loads the plan; the lanes of a
+//                       producer warp stream the live footprint rows through a ring of up to 8 stages
+//                       (cp.async.bulk global->shared, mbarrier complete_tx) — one lane per stage, or
+//                       one lane per sample for the 1-2 pixel pieces of a wide RoI, because the bulk
+//                       copies of ONE thread complete one at a time (~750 cycles each, measured).  C/2
+//                       consumer threads own two adjacent channels each (packed fp32 FFMA2), keep the
+//                       49 pooled values of both in registers and hand stages back through per-stage
 //                       mbarriers — warps never wait for each other inside an RoI.  The pooled
 //                       [C][49] block is staged in shared memory and leaves as ONE bulk store.
-//   msroi_bwd_tma       persistent, cooperative launch.  The producer prefetches the RoI's
-//                       [C][49] gradient block; consumers assemble each live footprint row in shared
-//                       memory and add it to the gradient map with ONE cp.reduce.async.bulk (SASS
-//                       UBLKRED): the L2 does the read-modify-write.  (The per-tap kernel issued 16
-//                       RED per output element and was bound by the SM's RED issue rate, ~1.3
-//                       cycles per lane.)  A third warp role zero-fills this CTA's share of the
-//                       gradient maps image by image, a bounded distance ahead of the consumers; an
-//                       RoI of image b waits for zero_done[b] == gridDim.x, so the maps need no
-//                       memset and no grid-wide barrier.
+//   msroi_bwd_tma       persistent, cooperative launch.  A driver lane prefetches each RoI's plan and
+//                       [C][49] gradient block; consumer warps assemble every live footprint row in
+//                       shared memory and hand it over through an mbarrier; the driver adds it to the
+//                       gradient map with ONE cp.reduce.async.bulk (SASS UBLKRED: the L2 does the
+//                       read-modify-write) and publishes which row buffers have been read.  (The
+//                       per-tap kernel issued 16 RED per output element and was bound by the SM's RED
+//                       issue rate, ~1.3 cycles per lane.)  A third warp role zero-fills this CTA's
+//                       share of the gradient maps image by image, a bounded distance ahead of the
+//                       reductions; an RoI of image b waits for zero_done[b] == gridDim.x, so the maps
+//                       need no memset and no grid-wide barrier.
 //
 // Arithmetic: bilinear pooling is separable.  With A_y[y][ph] = sum over the sampling rows of bin
 // ph of the weight they put on feature row y (and the column taps likewise),
@@ -38,9 +41,10 @@
 // mode").  The summation order differs from the CPU kernel's sample-by-sample order: results agree
 // to fp32 rounding (tests: 1e-5 relative), not bitwise.
 //
-// Roofline: HBM (SURVEY.md §8d byte model).  Measured on B200 (tools/microbench/tma_bulk.cu): bulk
-// reduce 5.8 TB/s into an L2-resident region, 3.0 TB/s into a 400 MB one (DRAM read-modify-write);
-// bulk load up to 17 TB/s on L2 hits; bulk store 7.3 TB/s.
+// Roofline: HBM (SURVEY.md §8d byte model).  Measured on B200 (tools/microbench/): bulk reduce
+// 5.8 TB/s into an L2-resident region, 3.0 TB/s into a 400 MB one (DRAM read-modify-write), engine
+// ceiling 23 B/clk/SM; bulk load up to 21 TB/s on L2 hits with >= 4 issuing lanes per SM (6.3 TB/s
+// with one); bulk store 7.3 TB/s.  profiles/README.md has the per-component timings of both kernels.
 #include "roi_common.cuh"
 
 namespace dgod {

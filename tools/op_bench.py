@@ -133,6 +133,18 @@ def bench_roi(args, out):
                 out.append(row("torchvision_msroi_bwd", f"B{B} {per}/img f32-nchw", us, K * C * 49 * 4 + 20 * K + fbytes))
 
 
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e-3      # CUDA-core fp32 peak of a B200
+
+
+def pair_stats(run_sizes):
+    """NMS is O(n^2) pair tests over O(n) bytes: pair evaluations per second and, at ~14 flop per
+    pair, the fraction of the fp32 CUDA-core peak, from the kernel time of the row being built."""
+    pairs = sum(r * (r - 1) // 2 for r in run_sizes)
+    k_us = LAST_KERNEL_US or 1.0
+    return {"pairs": pairs, "Gpairs/s": round(pairs / 1e3 / k_us, 2),
+            "frac_of_fp32_peak": round(pairs * 14 / 1e6 / k_us / FP32_PEAK_TFLOPS, 4)}
+
+
 def bench_nms(args, out):
     for n in args.nms:
         g = synth.gen(n)
@@ -142,7 +154,8 @@ def bench_nms(args, out):
         keep = ops.batched_nms(boxes, scores, idxs, 0.7)
         nb = 28 * n + 8 * keep.numel()
         us = time_op(lambda: ops.nms_segments(boxes, scores, idxs, [n], 0.7), args.iters)
-        out.append(row("batched_nms", f"{n} boxes, 5 groups, thr 0.7", us, nb, {"kept": keep.numel()}))
+        out.append(row("batched_nms", f"{n} boxes, 5 groups, thr 0.7", us, nb,
+                       {"kept": keep.numel(), **pair_stats(torch.bincount(idxs.cpu()).tolist())}))
         if args.tv:
             import torchvision
             us = time_op(lambda: torchvision.ops.batched_nms(boxes, scores, idxs, 0.7), args.iters)
@@ -155,7 +168,8 @@ def bench_nms(args, out):
     scores = synth.distinct_scores(n, g).to(DEV)
     idxs = torch.randint(0, 5, (n,), generator=g).to(DEV)
     us = time_op(lambda: ops.nms_segments(boxes, scores, idxs, counts, 0.7, max_out_per_seg=2000), args.iters)
-    out.append(row("batched_nms", "8 images x 8304 boxes, 5 groups (one call)", us, 28 * n + 8 * 8 * 2000))
+    runs = [c for i in range(8) for c in torch.bincount(idxs[i * 8304:(i + 1) * 8304].cpu(), minlength=5).tolist()]
+    out.append(row("batched_nms", "8 images x 8304 boxes, 5 groups (one call)", us, 28 * n + 8 * 8 * 2000, pair_stats(runs)))
 
 
 def bench_match(args, out):
@@ -245,7 +259,7 @@ def main():
     p.add_argument("--height", type=int, default=608)
     p.add_argument("--width", type=int, default=1024)
     p.add_argument("--rois", type=lambda s: [int(x) for x in s.split(",")], default=[512, 2048])
-    p.add_argument("--nms", type=lambda s: [int(x) for x in s.split(",")], default=[1000, 10000, 100000])
+    p.add_argument("--nms", type=lambda s: [int(x) for x in s.split(",")], default=[1000, 3000, 10000, 30000, 100000])
     p.add_argument("--tv", action="store_true")
     p.add_argument("--json", default="")
     args = p.parse_args()
