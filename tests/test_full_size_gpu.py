@@ -128,3 +128,29 @@ def test_msroi_align_8192_rois_linearity_and_adjoint():
     sel = torch.arange(0, B * per, 997)
     ref = O.msroi_align_fwd([x.detach().cpu().contiguous().numpy() for x in xs], rois[sel].cpu().numpy(), scales, 7, 7, 2, 2, 5)
     np.testing.assert_allclose(fx[sel].cpu().numpy(), ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+
+
+def test_msroi_align_repeated_launches_agree():
+    """The persistent backward (driver lane / row_full mbarriers / rows_released, zero-fill warp, bulk reductions) and
+    the multi-lane forward at bench.py's shape, 25 launches back to back with a dirty output buffer in between: every
+    result equals the first up to the reduction order (an intermittent hand-off race would show as a large error)."""
+    ops = _ops()
+    B, C, H, W, per = 8, 256, 608, 1024, 512
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+    xs = [f.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for f in synth.random_features(B, C, H, W, 0)]
+    rois = synth.rois_from_boxes([synth.random_boxes(per, H, W, synth.gen(10 + i)) for i in range(B)]).to(DEV)
+    offs = ops._offsets([per] * B, DEV)
+    go = torch.randn(B * per, C, 7, 7, generator=synth.gen(99)).to(DEV)
+    first_out = first_grads = None
+    for it in range(25):
+        out = ops.multiscale_roi_align(xs, rois, scales, 7, 2, 2, 5, roi_img_offsets=offs)
+        for x in xs:
+            x.grad = None
+        out.backward(go)
+        if first_out is None:
+            first_out, first_grads = out.detach().clone(), [x.grad.clone() for x in xs]
+            scale = [float(g.abs().max()) for g in first_grads]
+            continue
+        assert torch.equal(out.detach(), first_out)                      # the forward is deterministic
+        for x, g0, s in zip(xs, first_grads, scale):
+            assert float((x.grad - g0).abs().max()) <= 2e-6 * s
