@@ -140,6 +140,7 @@ int launch_nms_mask(const float4* sbox, const uint32_t* runkey, int n_pos, int m
 // the next chunk's rows stream in while this one is resolved — thread 0 walks the alive bits of
 // the diagonal word, then every thread ORs the kept rows of its word into the removed-bitmap.
 constexpr int kScanThreads = 256;
+constexpr int kScanThreadsLong = 1024;   // runs whose mask rows do not fit shared memory
 constexpr int kScanMaxWords = 160;   // runs up to ~10k candidates use the staged path
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
@@ -147,7 +148,7 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
 }
 
-__global__ void __launch_bounds__(kScanThreads)
+__global__ void __launch_bounds__(kScanThreadsLong)
 nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long long* __restrict__ diag_cols,
                 int row_words, const uint32_t* __restrict__ runkey, const uint8_t* __restrict__ alive, int n_pos,
                 unsigned long long* __restrict__ keepbits, int32_t* __restrict__ compact_pos,
@@ -235,7 +236,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
       const unsigned long long kept = s_kept;
       if (staged) {
         // 8 threads per word: each ORs every 8th kept row, then a 3-step shuffle OR
-        for (int w0 = 1; cc + w0 <= ce; w0 += kScanThreads / 8) {
+        for (int w0 = 1; cc + w0 <= ce; w0 += blockDim.x / 8) {
           const int w = w0 + (tid >> 3), part = tid & 7;
           unsigned long long acc = 0ull;
           if (cc + w <= ce) {
@@ -252,21 +253,30 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
           if (part == 0 && cc + w <= ce) s_removed[cc - cs + w] |= acc;
         }
       } else {
-        for (int w = tid + 1; cc + w <= ce; w += blockDim.x) {
-          unsigned long long acc = 0ull, kk = kept;
-          while (kk) {   // four independent loads in flight per step
-            unsigned long long v[4] = {0ull, 0ull, 0ull, 0ull};
+        // long runs: the rows stay in global memory (L2).  8 threads per word, each with its up to 8 kept rows
+        // in flight at once, then a 3-step shuffle OR; the launch uses 1024 threads for this path.
+        for (int w0 = 1; cc + w0 <= ce; w0 += blockDim.x / 8) {
+          const int w = w0 + (tid >> 3), part = tid & 7;
+          unsigned long long acc = 0ull;
+          if (cc + w <= ce) {
+            unsigned long long kk = kept & (0x0101010101010101ull << part);
+            unsigned long long v[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
+              v[u] = 0ull;
               if (kk) {
                 const int b = __ffsll((long long)kk) - 1;
                 kk &= kk - 1;
                 v[u] = mask[(size_t)(cc * 64 + b) * row_words + w];
               }
             }
-            acc |= (v[0] | v[1]) | (v[2] | v[3]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc |= v[u];
           }
-          s_removed[cc - cs + w] |= acc;
+          acc |= __shfl_xor_sync(0xffffffffu, acc, 1);
+          acc |= __shfl_xor_sync(0xffffffffu, acc, 2);
+          acc |= __shfl_xor_sync(0xffffffffu, acc, 4);
+          if (part == 0 && cc + w <= ce) s_removed[cc - cs + w] |= acc;
         }
       }
       if (tid < 64 && ((kept >> tid) & 1ull) && compact_pos) {
@@ -292,7 +302,7 @@ int launch_nms_scan(const unsigned long long* mask, const unsigned long long* di
     DGOD_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  nms_scan_kernel<<<cdiv(n_pos, 64), kScanThreads, smem, st>>>(mask, diag_cols, row_words, runkey, alive, n_pos, keepbits,
+  nms_scan_kernel<<<cdiv(n_pos, 64), staged ? kScanThreads : kScanThreadsLong, smem, st>>>(mask, diag_cols, row_words, runkey, alive, n_pos, keepbits,
                                                               compact_pos, run_count, staged);
   DGOD_LAUNCHED();
   return DGOD_OK;
