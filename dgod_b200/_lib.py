@@ -73,6 +73,8 @@ SIGNATURES = {
     "dgod_detect_candidates": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, f32, f32, f32,
                                      f32, f32, vp, vp, vp, vp, vp]),
     "dgod_grl_scale": (i32, [vp, vp, i64, f32, i32, vp]),
+    "dgod_image_batch": (i32, [C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), i32, i32,
+                               C.POINTER(f32), C.POINTER(f32), vp, i32, i32, vp]),
     "dgod_nchw_to_nhwc": (i32, [vp, vp, i32, i32, i32, i32, vp]),
 }
 

@@ -1,0 +1,91 @@
+// Input side of the detector: GeneralizedRCNNTransform.forward
+// (TV models/detection/transform.py:102-153, constructed at fasterrcnn.py:439-441 / fcos.py:483) —
+//   normalize   (image - mean[:,None,None]) / std[:,None,None]                      (transform.py:155-166)
+//   resize      F.interpolate(bilinear, align_corners=False, recompute_scale_factor=True)  (transform.py:25-83)
+//   batch       zero-padded copy into [B, C, H_pad, W_pad], sizes rounded up to 32     (transform.py:237-255)
+// as ONE launch for the whole batch.  The reference runs ~50 launches per batch (a normalize pair, an
+// interpolate and a padded copy per image): 1.7 ms on a B200, host-bound.  Algorithmic bytes:
+// sum_i C*h_i*w_i*4 read + B*C*H_pad*W_pad*4 written (102 + 60 MB at 8 x 3x800x1333 -> 608x1024): HBM-bound.
+//
+// Source coordinates follow ATen's upsample_bilinear2d (area_pixel_compute_source_index, align_corners
+// false): src = max(fma(scale, dst+0.5, -0.5), 0) with scale = in/out in fp32, i0 = (int)src, i1 = i0 + (i0 < in-1),
+// l1 = src - i0, l0 = 1 - l1, value = l0y*(l0x*v00 + l1x*v01) + l1y*(l0x*v10 + l1x*v11) on the normalised taps.
+#include "common.cuh"
+
+namespace dgod {
+
+constexpr int kMaxBatchImages = 16;   // per launch (pointers and sizes travel as kernel parameters)
+
+struct ImageBatchParams {
+  const float* img[kMaxBatchImages];
+  int in_h[kMaxBatchImages], in_w[kMaxBatchImages], out_h[kMaxBatchImages], out_w[kMaxBatchImages];
+  float mean[4], std[4];
+  int channels, pad_h, pad_w;
+};
+
+__global__ void __launch_bounds__(256)
+image_batch_kernel(const ImageBatchParams p, float* __restrict__ out, int first_image) {
+  const int b = blockIdx.z, y = blockIdx.y;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= p.pad_w) return;
+  const int ih = p.in_h[b], iw = p.in_w[b], oh = p.out_h[b], ow = p.out_w[b];
+  float* dst = out + ((size_t)(first_image + b) * p.channels * p.pad_h + y) * p.pad_w + x;
+  const size_t cstride_out = (size_t)p.pad_h * p.pad_w;
+  if (y >= oh || x >= ow) {          // the padding of batch_images
+    for (int c = 0; c < p.channels; ++c) dst[c * cstride_out] = 0.f;
+    return;
+  }
+  const float sy = (float)ih / (float)oh, sx = (float)iw / (float)ow;
+  // ATen evaluates scale*(dst+0.5)-0.5 as one fused multiply-add (both its CPU and CUDA kernels contract it)
+  const float fy = fmaxf(__fmaf_rn(sy, (float)y + 0.5f, -0.5f), 0.f), fx = fmaxf(__fmaf_rn(sx, (float)x + 0.5f, -0.5f), 0.f);
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < ih - 1 ? 1 : 0), x1 = x0 + (x0 < iw - 1 ? 1 : 0);
+  const float ly1 = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx1 = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
+  const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  const float* src = p.img[b];
+  const size_t cstride_in = (size_t)ih * iw;
+  for (int c = 0; c < p.channels; ++c) {
+    const float* s = src + c * cstride_in;
+    const float m = p.mean[c], sd = p.std[c];
+    float v00 = __ldg(s + (size_t)y0 * iw + x0), v01 = __ldg(s + (size_t)y0 * iw + x1);
+    float v10 = __ldg(s + (size_t)y1 * iw + x0), v11 = __ldg(s + (size_t)y1 * iw + x1);
+    if (m != 0.f || sd != 1.f) {     // (v - 0) / 1 == v exactly: DGFRCNN's transform (fasterrcnn.py:439-441) skips 12 IEEE divisions per pixel
+      v00 = (v00 - m) / sd; v01 = (v01 - m) / sd; v10 = (v10 - m) / sd; v11 = (v11 - m) / sd;
+    }
+    dst[c * cstride_out] = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+  }
+}
+
+}  // namespace dgod
+
+using namespace dgod;
+
+extern "C" int dgod_image_batch(const float* const* images, const int* in_h, const int* in_w, const int* out_h,
+                                const int* out_w, int n_img, int channels, const float* mean, const float* std,
+                                float* out, int pad_h, int pad_w, dgod_stream_t stream) {
+  DGOD_REQUIRE(n_img >= 0 && channels >= 1 && channels <= 4 && pad_h > 0 && pad_w > 0, "dgod_image_batch: bad size");
+  if (n_img == 0) return DGOD_OK;
+  DGOD_REQUIRE(images && in_h && in_w && out_h && out_w && mean && std && out, "dgod_image_batch: null pointer");
+  for (int first = 0; first < n_img; first += kMaxBatchImages) {
+    const int n = n_img - first < kMaxBatchImages ? n_img - first : kMaxBatchImages;
+    ImageBatchParams p = {};
+    for (int i = 0; i < n; ++i) {
+      const int k = first + i;
+      DGOD_REQUIRE(images[k] && in_h[k] > 0 && in_w[k] > 0 && out_h[k] > 0 && out_w[k] > 0 && out_h[k] <= pad_h &&
+                       out_w[k] <= pad_w,
+                   "dgod_image_batch: image %d has an empty or oversized shape", k);
+      p.img[i] = images[k];
+      p.in_h[i] = in_h[k]; p.in_w[i] = in_w[k]; p.out_h[i] = out_h[k]; p.out_w[i] = out_w[k];
+    }
+    for (int c = 0; c < channels; ++c) {
+      DGOD_REQUIRE(std[c] != 0.f, "dgod_image_batch: zero std");
+      p.mean[c] = mean[c];
+      p.std[c] = std[c];
+    }
+    p.channels = channels; p.pad_h = pad_h; p.pad_w = pad_w;
+    dim3 grid(cdiv(pad_w, 256), pad_h, n);
+    image_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, out, first);
+    DGOD_LAUNCHED();
+  }
+  return DGOD_OK;
+}

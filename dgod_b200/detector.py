@@ -298,12 +298,51 @@ class RoIHeads(nn.Module):
         return det, losses, box_features, label_list
 
 
+# ------------------------------------------------------------------------------------ input side
+class FusedTransform(GeneralizedRCNNTransform):
+    """GeneralizedRCNNTransform (TV models/detection/transform.py:102-153; fasterrcnn.py:439-441, fcos.py:483)
+    with normalize + resize + batch in ONE launch (`ops.image_batch`) instead of ~50, and
+    the box targets rescaled by one multiply per image.  `postprocess` (eval) is torchvision's."""
+
+    def forward(self, images: List[Tensor], targets: Optional[List[Dict[str, Tensor]]] = None):
+        images = list(images)
+        if targets is not None and any(("masks" in t or "keypoints" in t) for t in targets):
+            return super().forward(images, targets)        # not on DGOD's path (boxes and labels only)
+        if self.training and len(self.min_size) > 1:       # transform.py:168-175: random scale choice in training
+            k = int(torch.empty(1).uniform_(0.0, float(len(self.min_size))).item())
+            size = self.min_size[k]
+        else:
+            size = self.min_size[-1]
+        batched, sizes = ops.image_batch(images, self.image_mean, self.image_std, size, self.max_size, self.size_divisible)
+        if targets is not None:
+            out_targets = []
+            for img, t, (oh, ow) in zip(images, targets, sizes):
+                t = dict(t)                                # transform.py:112-120 copies the dicts
+                t["boxes"] = t["boxes"] * self._ratios(int(img.shape[-2]), int(img.shape[-1]), oh, ow, t["boxes"])
+                out_targets.append(t)
+            targets = out_targets
+        from torchvision.models.detection.image_list import ImageList
+        return ImageList(batched, [(int(h), int(w)) for h, w in sizes]), targets
+
+    def _ratios(self, h: int, w: int, oh: int, ow: int, like: Tensor) -> Tensor:
+        """resize_boxes (transform.py:305-316): fp32 ratios new/orig per axis, cached on the device."""
+        key = (h, w, oh, ow, like.device, like.dtype)
+        cache = self.__dict__.setdefault("_ratio_cache", {})
+        r = cache.get(key)
+        if r is None:
+            rh = torch.tensor(float(oh), dtype=torch.float32) / torch.tensor(float(h), dtype=torch.float32)
+            rw = torch.tensor(float(ow), dtype=torch.float32) / torch.tensor(float(w), dtype=torch.float32)
+            r = torch.stack([rw, rh, rw, rh]).to(device=like.device, dtype=like.dtype)
+            cache[key] = r
+        return r
+
+
 # ------------------------------------------------------------------------------------ detector
 class FasterRCNN(nn.Module):
     def __init__(self, num_classes: int = 9, min_size: int = 800, max_size: int = 1333,
                  trainable_backbone_layers: int = 5, rpn_batch_size_per_image=256, box_batch_size_per_image=512):
         super().__init__()
-        self.transform = GeneralizedRCNNTransform(min_size, max_size, [0.0, 0.0, 0.0], [1.0, 1.0, 1.0])  # fasterrcnn.py:439-441
+        self.transform = FusedTransform(min_size, max_size, [0.0, 0.0, 0.0], [1.0, 1.0, 1.0])  # fasterrcnn.py:439-441
         self.backbone = resnet_fpn_backbone(backbone_name="resnet50", weights=None,
                                             trainable_layers=trainable_backbone_layers)   # fasterrcnn.py:317
         oc = self.backbone.out_channels

@@ -29,6 +29,7 @@ from torchvision.ops import misc as misc_nn_ops
 from torchvision.ops.feature_pyramid_network import LastLevelP6P7
 
 from . import ops
+from .detector import FusedTransform
 
 
 # --------------------------------------------------------------------------------- detector
@@ -84,6 +85,9 @@ class FCOS(_TVFCOS):
         head.load_state_dict(self.head.state_dict())
         self.head = head
         self.num_classes = num_classes
+        t = self.transform                                   # fcos.py:483 -> the one-launch transform
+        self.transform = FusedTransform(t.min_size, t.max_size, t.image_mean, t.image_std, size_divisible=t.size_divisible,
+                                        fixed_size=t.fixed_size)
 
     def compute_loss(self, targets, head_outputs, anchors, num_anchors_per_level):
         # fcos.py:503-550: anchors are identical for every image of a batch (one padded size)

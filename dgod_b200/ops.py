@@ -322,6 +322,48 @@ def match_boxes(gt_boxes: Sequence[Tensor], boxes, high_threshold: float, low_th
     return out
 
 
+# --------------------------------------------------------------------------------- input side
+def resized_shape(h: int, w: int, min_size: int, max_size: int) -> Tuple[int, int]:
+    """Output size of TV transform.py:25-83 in eager mode: floor(in * min(min_size/min(h,w), max_size/max(h,w)))
+    (double arithmetic, as `interpolate(scale_factor=..., recompute_scale_factor=True)` computes it)."""
+    sf = min(float(min_size) / float(min(h, w)), float(max_size) / float(max(h, w)))
+    return int(math.floor(float(h) * sf)), int(math.floor(float(w) * sf))
+
+
+def image_batch(images: Sequence[Tensor], image_mean: Sequence[float], image_std: Sequence[float], min_size: int,
+                max_size: int, size_divisible: int = 32):
+    """GeneralizedRCNNTransform.forward for the images of a batch (TV transform.py:102-153: normalize,
+    resize, batch_images) in one launch.  images: CUDA fp32 [C,H,W] tensors (sizes may differ).  Returns
+    (batched [B,C,H_pad,W_pad] NCHW tensor, [(h_i, w_i)] resized sizes) — what `ImageList` holds."""
+    _need_cuda(*images)
+    lib = _lib.load()
+    n = len(images)
+    if n == 0:
+        raise RuntimeError("image_batch: empty batch")
+    imgs = []
+    for im in images:
+        if im.dim() != 3 or im.dtype != torch.float32:
+            raise RuntimeError(f"image_batch: images are expected to be float32 [C, H, W] tensors, got {tuple(im.shape)} {im.dtype}")
+        imgs.append(im.contiguous())
+    Cn = imgs[0].shape[0]
+    if Cn > 4 or Cn != len(image_mean) or Cn != len(image_std):
+        raise RuntimeError("image_batch: 1-4 channels with one mean / std each expected")
+    in_h, in_w = [int(i.shape[1]) for i in imgs], [int(i.shape[2]) for i in imgs]
+    sizes = [resized_shape(h, w, min_size, max_size) for h, w in zip(in_h, in_w)]
+    stride = float(size_divisible)
+    pad_h = int(math.ceil(max(s[0] for s in sizes) / stride) * stride)      # transform.py:242-247
+    pad_w = int(math.ceil(max(s[1] for s in sizes) / stride) * stride)
+    out = torch.empty((n, Cn, pad_h, pad_w), dtype=torch.float32, device=imgs[0].device)
+    ptrs = (C.c_void_p * n)(*[i.data_ptr() for i in imgs])
+    ia = lambda v: (C.c_int * n)(*v)
+    fa = lambda v: (C.c_float * Cn)(*[float(x) for x in v])
+    tok = KernelTimer.start("image_batch", sum(Cn * h * w * 4 for h, w in zip(in_h, in_w)) + out.numel() * 4)
+    check(lib.dgod_image_batch(ptrs, ia(in_h), ia(in_w), ia([s[0] for s in sizes]), ia([s[1] for s in sizes]), n, Cn,
+                               fa(image_mean), fa(image_std), _p(out), pad_h, pad_w, _stream()))
+    KernelTimer.stop(tok)
+    return out, sizes
+
+
 # --------------------------------------------------------------------------------- FCOS
 @torch.library.custom_op("dgod_b200::fcos_assign", mutates_args=())
 def _fcos_assign_op(anchors: Tensor, n_first: int, n_last: int, radius: float, gt_boxes: Tensor,

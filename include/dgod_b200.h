@@ -26,6 +26,8 @@
  *   dgod_box_decode         TV _utils.py:162-224 (TV roi_heads.py:692, fasterrcnn.py:294)
  *   dgod_detect_candidates  TV roi_heads.py:692-724 (softmax, clip, score/size filters)
  *   dgod_grl_scale          DGcommon.py:33-45 (GRLayer.backward)
+ *   dgod_image_batch        TV models/detection/transform.py:102-255 (GeneralizedRCNNTransform: normalize, resize, batch;
+ *                           fasterrcnn.py:439-441, fcos.py:483)
  *   dgod_nchw_to_nhwc       layout helper (no reference counterpart: torch's .contiguous(channels_last))
  */
 #ifndef DGOD_B200_H_
@@ -256,6 +258,18 @@ int dgod_detect_candidates(const float* class_logits /*[n_rows,n_cls]*/,
                            float score_thresh, float min_size,
                            float* cand_boxes, float* cand_scores, int64_t* cand_labels,
                            uint8_t* cand_valid, dgod_stream_t stream);
+
+/* ------------------------------------------------------------------ input side */
+
+/* GeneralizedRCNNTransform.forward for a batch in one launch: per image normalize with mean/std (host
+ * [channels], channels <= 4), bilinear resize [channels,in_h,in_w] -> [out_h,out_w] with ATen's
+ * align_corners=False source coordinates (scale = in/out), written zero-padded into
+ * out [n_img, channels, pad_h, pad_w] (NCHW, fully overwritten).  images: host array of device pointers
+ * to contiguous fp32 [channels, in_h, in_w]; the size arrays are host arrays.  The caller computes out_h /
+ * out_w (floor(in * min(min_size/min(h,w), max_size/max(h,w))), TV transform.py:25-83) and the padded size. */
+int dgod_image_batch(const float* const* images, const int* in_h, const int* in_w, const int* out_h,
+                     const int* out_w, int n_img, int channels, const float* mean, const float* std,
+                     float* out, int pad_h, int pad_w, dgod_stream_t stream);
 
 /* ------------------------------------------------------------------ layout */
 

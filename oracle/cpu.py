@@ -141,6 +141,27 @@ def fcos_loss(cls_logits, bbox_regression, bbox_ctrness, anchors, cls_targets, b
     return out
 
 
+def image_batch(images, mean, std, min_size, max_size, size_divisible=32):
+    """GeneralizedRCNNTransform.forward for a list of [C,H,W] images -> ([B,C,Hp,Wp] float32, [(h,w)])."""
+    import math
+    imgs = [_f32(i) for i in images]
+    sizes = []
+    for im in imgs:
+        h, w = im.shape[1:]
+        sf = min(float(min_size) / min(h, w), float(max_size) / max(h, w))
+        sizes.append((int(math.floor(h * sf)), int(math.floor(w * sf))))
+    ph = int(math.ceil(max(s[0] for s in sizes) / float(size_divisible)) * size_divisible)
+    pw = int(math.ceil(max(s[1] for s in sizes) / float(size_divisible)) * size_divisible)
+    out = np.empty((len(imgs), imgs[0].shape[0], ph, pw), np.float32)
+    m, s_ = _f32(np.asarray(mean)), _f32(np.asarray(std))
+    for i, (im, (oh, ow)) in enumerate(zip(imgs, sizes)):
+        o = np.empty(out.shape[1:], np.float32)
+        lib().o_image_resize_pad(_p(im), C.c_int(im.shape[0]), C.c_int(im.shape[1]), C.c_int(im.shape[2]), C.c_int(oh),
+                                 C.c_int(ow), _p(m), _p(s_), _p(o), C.c_int(ph), C.c_int(pw))
+        out[i] = o
+    return out, sizes
+
+
 # ---------------------------------------------------------------------------------- RoIAlign
 def roi_align_fwd(x, rois, scale, ph, pw, sr, aligned=False):
     """torchvision::roi_align CPU forward (TV ops/roi_align.py:204-260)."""

@@ -521,3 +521,33 @@ def test_fcos_loss_tail_forward_backward():
     z = ops.fcos_loss(ho["cls_logits"].detach(), ho["bbox_regression"].detach(), ho["bbox_ctrness"].detach(), a, none, box_t)
     assert float(z[3]) == 0.0 and float(z[1]) == 0.0 and float(z[2]) == 0.0 and np.isfinite(float(z[0]))
 
+
+
+# ------------------------------------------------------------------------------- input side
+def test_image_batch_and_fused_transform():
+    """ops.image_batch / detector.FusedTransform == GeneralizedRCNNTransform (TV transform.py:102-153): against the C
+    oracle (pinned on torchvision's CPU transform) and against torchvision's own transform on the GPU, mixed sizes."""
+    from torchvision.models.detection.transform import GeneralizedRCNNTransform
+    from dgod_b200.detector import FusedTransform
+    ops = _ops()
+    g = synth.gen(21)
+    imgs = [torch.rand(3, h, w, generator=g) for h, w in [(200, 333), (150, 400), (260, 180), (97, 101)]]
+    boxes = [synth.random_boxes(4, im.shape[1], im.shape[2], g) for im in imgs]
+    for (mn, mx, mean, std) in [(150, 300, [0.0, 0.0, 0.0], [1.0, 1.0, 1.0]), (224, 260, [0.485, 0.456, 0.406], [0.229, 0.224, 0.225])]:
+        ref, sizes = O.image_batch([i.numpy() for i in imgs], mean, std, mn, mx)
+        got, got_sizes = ops.image_batch([i.to(DEV) for i in imgs], mean, std, mn, mx)
+        assert got_sizes == sizes and tuple(got.shape) == ref.shape
+        np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=0, atol=1e-6)
+        for train in (True, False):
+            tv = GeneralizedRCNNTransform(mn, mx, mean, std).to(DEV).train(train)
+            mine = FusedTransform(mn, mx, mean, std).to(DEV).train(train)
+            targets = [{"boxes": b.to(DEV), "labels": torch.ones(4, dtype=torch.int64, device=DEV)} for b in boxes]
+            il_tv, tg_tv = tv([i.to(DEV) for i in imgs], [dict(t) for t in targets])
+            il, tg = mine([i.to(DEV) for i in imgs], [dict(t) for t in targets])
+            assert il.image_sizes == il_tv.image_sizes and il.tensors.shape == il_tv.tensors.shape
+            torch.testing.assert_close(il.tensors, il_tv.tensors, rtol=0, atol=1e-6)
+            for a, b in zip(tg, tg_tv):
+                assert torch.equal(a["boxes"], b["boxes"]) and torch.equal(a["labels"], b["labels"])
+            assert torch.equal(targets[0]["boxes"], boxes[0].to(DEV))            # the caller's targets are not modified
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.image_batch(imgs, [0.0] * 3, [1.0] * 3, 150, 300)

@@ -272,3 +272,21 @@ def test_detect_candidates_and_grl():
     assert np.array_equal(cv.astype(bool), (cs > np.float32(0.05)) & (ws >= np.float32(1e-2)) & (hs >= np.float32(1e-2)))
     x = torch.randn(1000, generator=g)
     assert np.array_equal((x.neg() * 0.1).numpy(), O.grl_scale(x.numpy(), 0.1))
+
+
+def test_image_batch_matches_torchvision_transform():
+    """oracle o_image_resize_pad == GeneralizedRCNNTransform.forward (TV transform.py:102-153, the transform
+    fasterrcnn.py:439-441 / fcos.py:483 construct): mixed image sizes, both scale regimes, non-trivial mean/std."""
+    from torchvision.models.detection.transform import GeneralizedRCNNTransform
+    g = synth.gen(21)
+    imgs = [torch.rand(3, h, w, generator=g) for h, w in [(200, 333), (150, 400), (260, 180), (97, 101)]]
+    boxes = [synth.random_boxes(4, im.shape[1], im.shape[2], g) for im in imgs]
+    for (mn, mx, mean, std) in [(150, 300, [0.0, 0.0, 0.0], [1.0, 1.0, 1.0]), (224, 260, [0.485, 0.456, 0.406], [0.229, 0.224, 0.225])]:
+        tr = GeneralizedRCNNTransform(mn, mx, mean, std).eval()
+        il, tg = tr([i.clone() for i in imgs], [{"boxes": b.clone()} for b in boxes])
+        out, sizes = O.image_batch([i.numpy() for i in imgs], mean, std, mn, mx)
+        assert [tuple(s) for s in il.image_sizes] == sizes and tuple(il.tensors.shape) == out.shape
+        np.testing.assert_allclose(out, il.tensors.numpy(), rtol=0, atol=1e-6)     # 1-2 ulp: the blend's own rounding
+        for t, b, im, (oh, ow) in zip(tg, boxes, imgs, sizes):                       # resize_boxes, transform.py:305-316
+            r = torch.tensor([ow / im.shape[2], oh / im.shape[1]] * 2)
+            torch.testing.assert_close(t["boxes"], b * r, rtol=1e-6, atol=1e-4)

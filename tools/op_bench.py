@@ -228,6 +228,20 @@ def bench_fcos(args, out):
             out.append(row("torchvision_ops_fcos_loss fwd+bwd (ATen chain of fcos.py:149-202)", f"B8 {n} locations", t, 3 * alg))
 
 
+def bench_transform(args, out):
+    """GeneralizedRCNNTransform (TV transform.py:102-153) on 8 x 3x800x1333 -> 600x999 -> 608x1024."""
+    from dgod_b200.detector import FusedTransform
+    imgs = [i.to(DEV) for i in synth.random_images(8, 800, 1333, 0)]
+    nbytes = 8 * 3 * 800 * 1333 * 4 + 8 * 3 * 608 * 1024 * 4
+    us = time_op(lambda: ops.image_batch(imgs, [0.0] * 3, [1.0] * 3, 600, 1200), args.iters)
+    out.append(row("image_batch (normalize+resize+pad)", "8 x 3x800x1333 -> 608x1024", us, nbytes))
+    if args.tv:
+        from torchvision.models.detection.transform import GeneralizedRCNNTransform
+        tv = GeneralizedRCNNTransform(600, 1200, [0.0] * 3, [1.0] * 3).to(DEV)
+        us = time_op(lambda: tv(imgs), args.iters)
+        out.append(row("torchvision_transform", "8 x 3x800x1333 -> 608x1024", us, nbytes))
+
+
 def bench_rpn(args, out):
     cells = [c.tolist() for c in make_cell_anchors(((32,), (64,), (128,), (256,), (512,)), ((0.5, 1.0, 2.0),) * 5)]
     for (h, w) in [(608, 1024), (800, 1344)]:
@@ -253,7 +267,7 @@ def bench_grl(args, out):
 
 def main():
     p = argparse.ArgumentParser()
-    p.add_argument("--ops", default="roi,nms,match,fcos,rpn,grl")
+    p.add_argument("--ops", default="roi,nms,match,fcos,rpn,grl,transform")
     p.add_argument("--iters", type=int, default=20)
     p.add_argument("--batch", type=int, default=8)
     p.add_argument("--height", type=int, default=608)
@@ -264,7 +278,8 @@ def main():
     p.add_argument("--json", default="")
     args = p.parse_args()
     out = []
-    table = {"roi": bench_roi, "nms": bench_nms, "match": bench_match, "fcos": bench_fcos, "rpn": bench_rpn, "grl": bench_grl}
+    table = {"roi": bench_roi, "nms": bench_nms, "match": bench_match, "fcos": bench_fcos, "rpn": bench_rpn, "grl": bench_grl,
+             "transform": bench_transform}
     for name in args.ops.split(","):
         table[name](args, out)
     if args.json:
