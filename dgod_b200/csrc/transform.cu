@@ -23,37 +23,61 @@ struct ImageBatchParams {
   int channels, pad_h, pad_w;
 };
 
+constexpr int kPxPerThread = 4;       // consecutive output pixels per thread: one 128-bit store per channel
+
 __global__ void __launch_bounds__(256)
 image_batch_kernel(const ImageBatchParams p, float* __restrict__ out, int first_image) {
   const int b = blockIdx.z, y = blockIdx.y;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= p.pad_w) return;
+  const int xb = (blockIdx.x * blockDim.x + threadIdx.x) * kPxPerThread;      // pad_w is a multiple of 4
+  if (xb >= p.pad_w) return;
   const int ih = p.in_h[b], iw = p.in_w[b], oh = p.out_h[b], ow = p.out_w[b];
-  float* dst = out + ((size_t)(first_image + b) * p.channels * p.pad_h + y) * p.pad_w + x;
+  float* dst = out + ((size_t)(first_image + b) * p.channels * p.pad_h + y) * p.pad_w + xb;
   const size_t cstride_out = (size_t)p.pad_h * p.pad_w;
-  if (y >= oh || x >= ow) {          // the padding of batch_images
-    for (int c = 0; c < p.channels; ++c) dst[c * cstride_out] = 0.f;
+  if (y >= oh || xb >= ow) {          // the padding of batch_images
+    for (int c = 0; c < p.channels; ++c) *reinterpret_cast<float4*>(dst + c * cstride_out) = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
   }
   const float sy = (float)ih / (float)oh, sx = (float)iw / (float)ow;
   // ATen evaluates scale*(dst+0.5)-0.5 as one fused multiply-add (both its CPU and CUDA kernels contract it)
-  const float fy = fmaxf(__fmaf_rn(sy, (float)y + 0.5f, -0.5f), 0.f), fx = fmaxf(__fmaf_rn(sx, (float)x + 0.5f, -0.5f), 0.f);
-  const int y0 = (int)fy, x0 = (int)fx;
-  const int y1 = y0 + (y0 < ih - 1 ? 1 : 0), x1 = x0 + (x0 < iw - 1 ? 1 : 0);
-  const float ly1 = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx1 = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
-  const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  const float fy = fmaxf(__fmaf_rn(sy, (float)y + 0.5f, -0.5f), 0.f);
+  const int y0 = (int)fy;
+  const int y1 = y0 + (y0 < ih - 1 ? 1 : 0);
+  const float ly1 = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), ly0 = 1.f - ly1;
+  int x0[kPxPerThread], x1[kPxPerThread];
+  float lx0[kPxPerThread], lx1[kPxPerThread];
+#pragma unroll
+  for (int q = 0; q < kPxPerThread; ++q) {
+    const float fx = fmaxf(__fmaf_rn(sx, (float)(xb + q) + 0.5f, -0.5f), 0.f);
+    x0[q] = min((int)fx, iw - 1);                     // columns past out_w (zeroed below) must still read in range
+    x1[q] = x0[q] + (x0[q] < iw - 1 ? 1 : 0);
+    lx1[q] = fminf(fmaxf(fx - (float)x0[q], 0.f), 1.f);
+    lx0[q] = 1.f - lx1[q];
+  }
   const float* src = p.img[b];
   const size_t cstride_in = (size_t)ih * iw;
-  for (int c = 0; c < p.channels; ++c) {
-    const float* s = src + c * cstride_in;
-    const float m = p.mean[c], sd = p.std[c];
-    float v00 = __ldg(s + (size_t)y0 * iw + x0), v01 = __ldg(s + (size_t)y0 * iw + x1);
-    float v10 = __ldg(s + (size_t)y1 * iw + x0), v11 = __ldg(s + (size_t)y1 * iw + x1);
-    if (m != 0.f || sd != 1.f) {     // (v - 0) / 1 == v exactly: DGFRCNN's transform (fasterrcnn.py:439-441) skips 12 IEEE divisions per pixel
-      v00 = (v00 - m) / sd; v01 = (v01 - m) / sd; v10 = (v10 - m) / sd; v11 = (v11 - m) / sd;
+  const float* r0 = src + (size_t)y0 * iw;
+  const float* r1 = src + (size_t)y1 * iw;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    if (c < p.channels) {
+      float v[kPxPerThread][4];
+#pragma unroll
+      for (int q = 0; q < kPxPerThread; ++q) {        // the 16 taps of this channel in flight before the first blend
+        v[q][0] = __ldg(r0 + c * cstride_in + x0[q]); v[q][1] = __ldg(r0 + c * cstride_in + x1[q]);
+        v[q][2] = __ldg(r1 + c * cstride_in + x0[q]); v[q][3] = __ldg(r1 + c * cstride_in + x1[q]);
+      }
+      const float m = p.mean[c], sd = p.std[c];
+      float o[kPxPerThread];
+#pragma unroll
+      for (int q = 0; q < kPxPerThread; ++q) {
+        float v00 = v[q][0], v01 = v[q][1], v10 = v[q][2], v11 = v[q][3];
+        if (m != 0.f || sd != 1.f) {   // (v - 0) / 1 == v exactly: DGFRCNN's transform (fasterrcnn.py:439-441) skips the IEEE divisions
+          v00 = (v00 - m) / sd; v01 = (v01 - m) / sd; v10 = (v10 - m) / sd; v11 = (v11 - m) / sd;
+        }
+        o[q] = (xb + q < ow) ? ly0 * (lx0[q] * v00 + lx1[q] * v01) + ly1 * (lx0[q] * v10 + lx1[q] * v11) : 0.f;
+      }
+      *reinterpret_cast<float4*>(dst + c * cstride_out) = make_float4(o[0], o[1], o[2], o[3]);
     }
-    dst[c * cstride_out] = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
-  }
 }
 
 }  // namespace dgod
@@ -64,6 +88,7 @@ extern "C" int dgod_image_batch(const float* const* images, const int* in_h, con
                                 const int* out_w, int n_img, int channels, const float* mean, const float* std,
                                 float* out, int pad_h, int pad_w, dgod_stream_t stream) {
   DGOD_REQUIRE(n_img >= 0 && channels >= 1 && channels <= 4 && pad_h > 0 && pad_w > 0, "dgod_image_batch: bad size");
+  DGOD_REQUIRE(pad_w % 4 == 0 && ((uintptr_t)out & 15) == 0, "dgod_image_batch: pad_w must be a multiple of 4 and out 16-byte aligned");
   if (n_img == 0) return DGOD_OK;
   DGOD_REQUIRE(images && in_h && in_w && out_h && out_w && mean && std && out, "dgod_image_batch: null pointer");
   for (int first = 0; first < n_img; first += kMaxBatchImages) {
@@ -83,7 +108,7 @@ extern "C" int dgod_image_batch(const float* const* images, const int* in_h, con
       p.std[c] = std[c];
     }
     p.channels = channels; p.pad_h = pad_h; p.pad_w = pad_w;
-    dim3 grid(cdiv(pad_w, 256), pad_h, n);
+    dim3 grid(cdiv(pad_w, 256 * kPxPerThread), pad_h, n);
     image_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, out, first);
     DGOD_LAUNCHED();
   }
