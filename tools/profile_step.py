@@ -47,7 +47,12 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for s in range(8):
         step(res[(s // 2) % 4])
     torch.cuda.synchronize()
+from torch.autograd import DeviceType
+kern = [e for e in prof.events() if e.device_type == DeviceType.CUDA]
+gpu_ms = sum(e.device_time for e in kern) / 1e3
+ours = sum(e.device_time for e in kern if e.name.startswith("dgod::") or "dgod::" in e.name) / 1e3
+span = (max(e.time_range.end for e in kern) - min(e.time_range.start for e in kern)) / 1e3
+print(f"GPU kernels over the 8-step cycle: {len(kern)} launches, {gpu_ms:.1f} ms busy in a {span:.1f} ms span "
+      f"({100 * gpu_ms / span:.0f} % busy); dgod_b200 kernels {ours:.2f} ms")
 ka = prof.key_averages()
-gpu_ms = sum(e.self_device_time_total for e in ka) / 1e3
-print(f"sum of kernel time over the 8-step cycle: {gpu_ms:.1f} ms")
 print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=40, max_name_column_width=70))
