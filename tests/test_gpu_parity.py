@@ -551,3 +551,14 @@ def test_image_batch_and_fused_transform():
             assert torch.equal(targets[0]["boxes"], boxes[0].to(DEV))            # the caller's targets are not modified
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.image_batch(imgs, [0.0] * 3, [1.0] * 3, 150, 300)
+
+
+def test_image_batch_more_images_than_one_launch_takes():
+    """20 images (> 16 per launch): the second launch writes behind the first; single-channel input; tiny images."""
+    ops = _ops()
+    g = synth.gen(33)
+    imgs = [torch.rand(1, 40 + 3 * i, 55 + 2 * i, generator=g) for i in range(20)]
+    ref, sizes = O.image_batch([i.numpy() for i in imgs], [0.3], [0.7], 48, 80)
+    got, got_sizes = ops.image_batch([i.to(DEV) for i in imgs], [0.3], [0.7], 48, 80)
+    assert got_sizes == sizes
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=0, atol=1e-6)
