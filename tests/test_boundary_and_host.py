@@ -53,6 +53,16 @@ def test_workspace_queries_and_argument_errors_without_gpu():
     cfg.n_levels = 99
     rc = lib.dgod_msroi_align_fwd(ctypes.byref(cfg), None, None, 0, None, None, 0, None)
     assert rc == -1 and b"n_levels" in lib.dgod_last_error()
+    # the two SURVEY §8f entry points
+    assert lib.dgod_fcos_loss_workspace_bytes(8 * 22400) >= (8 * 22400 // 256) * 32
+    rc = lib.dgod_fcos_loss_fwd(None, None, None, None, None, None, 2, 100, 0, 0.25, None, None, 0, None)
+    assert rc == -1 and b"dgod_fcos_loss_fwd" in lib.dgod_last_error()
+    rc = lib.dgod_fcos_loss_bwd(None, None, None, None, None, None, 2, 100, 9, 0.25, None, None, None, None, None, None)
+    assert rc == -1 and b"null pointer" in lib.dgod_last_error()
+    assert lib.dgod_fcos_loss_bwd(None, None, None, None, None, None, 0, 100, 9, 0.25, None, None, None, None, None, None) == 0
+    rc = lib.dgod_image_batch(None, None, None, None, None, 3, 5, None, None, None, 32, 32, None)
+    assert rc == -1 and b"dgod_image_batch" in lib.dgod_last_error()
+    assert lib.dgod_image_batch(None, None, None, None, None, 0, 3, None, None, None, 32, 32, None) == 0
 
 
 def test_product_never_imports_the_oracle():
@@ -95,6 +105,22 @@ def test_custom_ops_are_registered_with_fake_kernels():
                                                  None, torch.empty(3, device="meta"), 30, 0.5, False, 10)
     assert keep.shape == (2, 10) and info.shape == (3,)
     assert "roi_img_offsets" in str(torch.ops.dgod_b200.msroi_align.default._schema)
+    m = lambda *shape, dtype=torch.float32: torch.empty(*shape, dtype=dtype, device="meta")
+    out = torch.ops.dgod_b200.fcos_loss(m(2, 50, 9), m(2, 50, 4), m(2, 50, 1), m(50, 4), m(2, 50, dtype=torch.int64), m(2, 50, 4), 0.25)
+    assert out.shape == (4,)
+    g = torch.ops.dgod_b200.fcos_loss_backward(m(2, 50, 9), m(2, 50, 4), m(2, 50, 1), m(50, 4), m(2, 50, dtype=torch.int64),
+                                               m(2, 50, 4), 0.25, m(4), m(3))
+    assert [tuple(t.shape) for t in g] == [(2, 50, 9), (2, 50, 4), (2, 50, 1)]
+
+
+def test_resized_shape_follows_torchvision():
+    """ops.resized_shape == the size torchvision's transform produces (TV transform.py:25-83), incl. both regimes."""
+    from torchvision.models.detection.transform import GeneralizedRCNNTransform
+    from dgod_b200 import ops
+    for (h, w, mn, mx) in [(800, 1333, 600, 1200), (600, 1200, 600, 1200), (97, 101, 224, 260), (333, 200, 150, 300), (720, 1280, 800, 1333)]:
+        tr = GeneralizedRCNNTransform(mn, mx, [0.0] * 3, [1.0] * 3).eval()
+        il, _ = tr([torch.zeros(3, h, w)])
+        assert il.image_sizes[0] == ops.resized_shape(h, w, mn, mx), (h, w, mn, mx)
 
 
 def test_patch_and_unpatch_rebind_the_reference_call_sites():
