@@ -15,6 +15,7 @@ LIB_PATH = PKG_DIR / "libdgod_b200.so"
 MAX_LEVELS = 8
 MAX_CELL_ANCHORS = 16
 F32, BF16 = 0, 1
+ABI_VERSION = 2   # DGOD_ABI_VERSION of include/dgod_b200.h
 
 vp, i32, i64, f32, f64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
 
@@ -68,6 +69,7 @@ SIGNATURES = {
     "dgod_msroi_align_fwd_workspace_bytes": (sz, [i32]),
     "dgod_msroi_align_fwd": (i32, [C.POINTER(RoiConfig), C.POINTER(vp), vp, i32, vp, vp, sz, vp]),
     "dgod_msroi_align_bwd_workspace_bytes": (sz, [i32]),
+    "dgod_msroi_align_bwd_workspace_bytes_cfg": (sz, [C.POINTER(RoiConfig), i32]),
     "dgod_msroi_align_bwd": (i32, [C.POINTER(RoiConfig), vp, vp, i32, vp, C.POINTER(vp), i32, vp, sz, vp]),
     "dgod_box_decode": (i32, [vp, vp, i32, i32, f32, f32, f32, f32, f32, vp, vp]),
     "dgod_detect_candidates": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, f32, f32, f32,
@@ -104,7 +106,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so is stale
         fn.restype = res
         fn.argtypes = args
-    if lib.dgod_abi_version() != 1:
+    if lib.dgod_abi_version() != ABI_VERSION:
         raise DgodError("dgod_b200: ABI version mismatch between _lib.py and libdgod_b200.so")
     _lib = lib
     return lib

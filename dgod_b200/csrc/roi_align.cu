@@ -173,6 +173,10 @@ int msroi_fwd_tma(const dgod_roi_config* cfg, const RoiDev& g, const float* rois
 int msroi_bwd_tma(const dgod_roi_config* cfg, const RoiDev& g, const void* grad_out, const float* rois, int n_rois,
                   void* workspace, size_t workspace_bytes, cudaStream_t st, int* handled);
 size_t msroi_tma_workspace(int n_rois);
+// owner-computes backward (roi_align_own.cu): channels_last, 7x7 bins, sampling ratio 1..2, C % 64 == 0
+int msroi_bwd_own(const dgod_roi_config* cfg, const RoiDev& g, const void* grad_out, const float* rois, int n_rois,
+                  const int32_t* roi_img_offsets, void* workspace, size_t workspace_bytes, cudaStream_t st, int* handled);
+size_t msroi_own_workspace(const RoiDev& g, int n_rois);
 
 // DGOD_FWD_ALGO=1 keeps the forward on the table-driven kernel (A/B measurements); default: TMA path first.
 static int fwd_algo_from_env() {
@@ -227,6 +231,16 @@ extern "C" size_t dgod_msroi_align_bwd_workspace_bytes(int n_rois) {
   return a > b ? a : b;
 }
 
+extern "C" size_t dgod_msroi_align_bwd_workspace_bytes_cfg(const dgod_roi_config* cfg, int n_rois) {
+  size_t need = dgod_msroi_align_bwd_workspace_bytes(n_rois);
+  RoiDev g;
+  if (cfg && fill_roi_dev(cfg, g) == DGOD_OK) {
+    const size_t own = msroi_own_workspace(g, n_rois);
+    if (own > need) need = own;
+  }
+  return need;
+}
+
 extern "C" int dgod_msroi_align_bwd(const dgod_roi_config* cfg, const void* grad_out,
                                     const float* rois, int n_rois,
                                     const int32_t* roi_img_offsets, void* const* grad_feats,
@@ -236,7 +250,7 @@ extern "C" int dgod_msroi_align_bwd(const dgod_roi_config* cfg, const void* grad
   int rc = fill_roi_dev(cfg, g);
   if (rc) return rc;
   DGOD_REQUIRE(n_rois >= 0, "roi_align: negative n_rois");
-  DGOD_REQUIRE(algo >= 0 && algo <= 3, "roi_align: unknown backward algorithm");
+  DGOD_REQUIRE(algo >= 0 && algo <= 4, "roi_align: unknown backward algorithm");
   DGOD_REQUIRE(grad_feats, "roi_align: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t esz = cfg->dtype == DGOD_F32 ? 4 : 2;
@@ -246,9 +260,16 @@ extern "C" int dgod_msroi_align_bwd(const dgod_roi_config* cfg, const void* grad
   }
   if (g.B == 0) return DGOD_OK;
   DGOD_REQUIRE(n_rois == 0 || (grad_out && rois), "roi_align: null pointer");
-  // algo 0 (auto): the TMA bulk-reduce path when the shape allows (channels_last, 7x7, sr 1..2), else
+  // algo 0 (auto): the owner-computes kernel when the shape allows (channels_last, 7x7, sr 1..2, C % 64 == 0) and the
+  // workspace was sized with dgod_msroi_align_bwd_workspace_bytes_cfg; else the TMA bulk-reduce path; else
   // fp32 gradients take the scatter path (16-byte vector reductions on channels_last, scalar atomics
   // on NCHW) and bf16 gradients the deterministic tile gather (fp32 accumulation, one rounding).
+  if (algo == 0 || algo == 4) {
+    int handled = 0;
+    rc = msroi_bwd_own(cfg, g, grad_out, rois, n_rois, roi_img_offsets, workspace, workspace_bytes, st, &handled);
+    if (rc || handled) return rc;
+    DGOD_REQUIRE(algo == 0, "roi_align: the owner-computes backward does not support this configuration or workspace");
+  }
   if (algo == 0 || algo == 3) {
     int handled = 0;
     rc = msroi_bwd_tma(cfg, g, grad_out, rois, n_rois, workspace, workspace_bytes, st, &handled);

@@ -169,6 +169,7 @@ class RegionProposalNetwork(nn.Module):
             m = ops.match_boxes([t["boxes"] for t in targets], anchors, self.fg_iou_thresh, self.bg_iou_thresh,
                                 True, want=("labels_f32", "matched_boxes"))  # fasterrcnn.py:187
             losses = self.compute_loss(objectness, deltas, m["labels_f32"], m["matched_boxes"], anchors, sampler_keys)
+            self.last_anchor_labels = m["labels_f32"]          # [B, A] 1 / 0 / -1 (tests compare them with the golden)
         return (boxes, scores, counts), losses
 
     def compute_loss(self, objectness, deltas, labels, matched_gt_boxes, anchors, sampler_keys=None):
@@ -221,8 +222,6 @@ class RoIHeads(nn.Module):
                             gt_labels=gt_labels, want=("labels_i64", "clamped_idx"))
         B, N = len(proposals), max(sizes)
         S = self.batch_size_per_image
-        if min(sizes) < S:
-            raise RuntimeError(f"RoI sampling needs at least {S} proposals per image, got {min(sizes)}")
         dev = proposals[0].device
         if min(sizes) == N:                                                               # common case: no padding
             labels = m["labels_i64"].view(B, N)
@@ -235,32 +234,41 @@ class RoIHeads(nn.Module):
             for i, (l, c, p) in enumerate(zip(m["labels_i64"].split(sizes), m["clamped_idx"].split(sizes), proposals)):
                 labels[i, :sizes[i]], idxs[i, :sizes[i]], props[i, :sizes[i]] = l, c, p
         pos_idx, pos_valid, neg_idx, neg_valid = self.sampler(labels, sampler_keys)
-        big = torch.full_like(pos_idx, N)
-        chosen = torch.cat([torch.where(pos_valid, pos_idx, big),
+        chosen = torch.cat([torch.where(pos_valid, pos_idx, torch.full_like(pos_idx, N)),
                             torch.where(neg_valid, neg_idx, torch.full_like(neg_idx, N))], dim=1)
+        if chosen.shape[1] < S:                                # fewer candidates than slots: pad with the sentinel
+            chosen = torch.cat([chosen, torch.full((B, S - chosen.shape[1]), N, dtype=chosen.dtype, device=dev)], dim=1)
         sel = torch.sort(chosen, dim=1).values[:, :S]          # ascending index like torch.where (roi_heads.py:620)
+        # An image with fewer than S candidates (positives + negatives) leaves slots empty.  The reference would
+        # mis-split its batch there (fasterrcnn.py:211-212 hard-codes 512 rows per image); this mirror keeps the
+        # [B, S] shape DGFRCNN.py:152-153 relies on and marks the empty slots: label -100 (cross_entropy's
+        # ignore_index, also inside the DG heads), a zero box, excluded from both loss denominators.
+        slot_valid = sel < N
         sel = sel.clamp(max=N - 1)
-        s_props = torch.gather(props, 1, sel[..., None].expand(-1, -1, 4))
-        s_labels = torch.gather(labels, 1, sel)
-        s_idxs = torch.gather(idxs, 1, sel)
+        s_props = torch.gather(props, 1, sel[..., None].expand(-1, -1, 4)) * slot_valid[..., None]
+        s_labels = torch.where(slot_valid, torch.gather(labels, 1, sel), torch.full_like(sel, -100))
+        s_idxs = torch.gather(idxs, 1, sel) * slot_valid
         max_gt = max([g.shape[0] for g in gt_boxes] + [1])
         gt_pad = torch.zeros((B, max_gt, 4), dtype=props.dtype, device=dev)
         for i, g in enumerate(gt_boxes):
             gt_pad[i, :g.shape[0]] = g
         matched_gt = torch.gather(gt_pad, 1, s_idxs[..., None].expand(-1, -1, 4))
-        reg_targets = encode_boxes(matched_gt, s_props, self.weights)
+        safe = s_props.clone()
+        safe[..., 2:] += (~slot_valid)[..., None]              # empty slots encode against the box (0,0,1,1): log() stays finite
+        reg_targets = encode_boxes(matched_gt, safe, self.weights)
         return s_props, s_idxs, s_labels, reg_targets
 
     def losses(self, class_logits, box_regression, labels, regression_targets):
         """fastrcnn_loss per image (fasterrcnn.py:198-236)."""
         B, S = labels.shape
         C = class_logits.shape[-1]
-        cls = F.cross_entropy(class_logits, labels.reshape(-1), reduction="none").view(B, S).mean(1)
+        n_valid = (labels >= 0).sum(1).clamp(min=1).to(class_logits.dtype)      # == S unless slots are empty
+        cls = F.cross_entropy(class_logits, labels.reshape(-1), reduction="none").view(B, S).sum(1) / n_valid
         pos = labels > 0
         reg = box_regression.view(B, S, C, 4)
         picked = torch.gather(reg, 2, labels.clamp(min=0)[..., None, None].expand(-1, -1, 1, 4)).squeeze(2)
         tgt = torch.where(pos[..., None], regression_targets, torch.zeros_like(regression_targets))
-        box = (F.smooth_l1_loss(picked, tgt, beta=1 / 9, reduction="none").sum(-1) * pos).sum(1) / S
+        box = (F.smooth_l1_loss(picked, tgt, beta=1 / 9, reduction="none").sum(-1) * pos).sum(1) / n_valid
         return {"loss_classifier": cls, "loss_box_reg": box}
 
     def postprocess_detections(self, class_logits, box_regression, proposals, boxes_per_image, image_sizes_t):

@@ -81,7 +81,8 @@ class DGFRCNN(nn.Module):
     `batch` = (images list, boxes list, labels list, domain tensor) like DGcommon.collate_fn."""
 
     def __init__(self, n_classes: int, batch_size: int, exp: str, reg_weights: Sequence[float], num_domains: int,
-                 min_size: int = 600, max_size: int = 1200, batched_modes: bool = True):
+                 min_size: int = 600, max_size: int = 1200, batched_modes: bool = True,
+                 trainable_backbone_layers: int = 3):
         super().__init__()
         self.n_classes, self.batch_size, self.exp = n_classes, batch_size, exp
         # Modes 2-4 of the reference run B separate batch-1 detector passes (DGFRCNN.py:165,177,190).
@@ -89,13 +90,20 @@ class DGFRCNN(nn.Module):
         # batched pass + per-image slices of box_features / box_labels gives the same losses and
         # gradients with 1/B of the launches.  False = the reference's loop.
         self.batched_modes = batched_modes
+        # modes 2-4, batched: evaluate only the heads whose domain occurs in the batch (needs the domain ids on the
+        # host).  With the ids on the device and this flag off, every head is evaluated and masked instead (no host
+        # read; heads without a matching image then receive zero gradients rather than none).
+        self.exact_head_set = True
         self.reg_weights, self.num_domains = list(reg_weights), num_domains
         self.mode = 0
         self.sub_mode = 0
         self.InsDA = InstanceDA(num_domains)
         self.InsClsPrime = nn.ModuleList([InsClsPrime(n_classes) for _ in range(num_domains)])
         self.InsCls = nn.ModuleList([InsCls(n_classes) for _ in range(num_domains)])
-        self.detector = FasterRCNN(num_classes=n_classes, min_size=min_size, max_size=max_size)  # DGFRCNN.py:81
+        # DGFRCNN.py:81 -> fasterrcnn.py:307-329: the factory builds FastRCNNPredictor(in_features, num_classes + 1) (10 logits,
+        # 40 box outputs for the 9 of DGOD) and, with pretrained=True, keeps trainable_backbone_layers=3 (conv1 / layer1 frozen)
+        self.detector = FasterRCNN(num_classes=n_classes + 1, min_size=min_size, max_size=max_size,
+                                   trainable_backbone_layers=trainable_backbone_layers)
         self.ImageDA = ImageDAFPN(num_domains)
         self.base_lr, self.weight_decay = 2e-3, 0.0005
 
@@ -129,21 +137,35 @@ class DGFRCNN(nn.Module):
             self.sub_mode = 0
             self.mode = 0
 
-    def _instance_losses_batched(self, heads, domain: Tensor, own_domain: bool) -> Tensor:
+    def _instance_losses_batched(self, heads, domain: Tensor, own_domain: bool, dom_list=None) -> Tensor:
         """Per-(image, head) cross-entropy terms of modes 2-4 from ONE batched detector pass.
-        Every head scores every image's 512 RoI features; a device-side mask then keeps head
-        domain[i] for image i (own_domain) or all the other heads (mode 4) — no host read of the
-        domain ids.  Returns the mean over the kept terms (DGFRCNN.py:170,181,196)."""
+        A head scores every image's 512 RoI features; a device-side mask then keeps head domain[i] for image i
+        (own_domain) or all the other heads (mode 4).  Only the heads the reference's per-image loop would touch are
+        evaluated (`dom_list`, the domain ids on the host — the reference reads them with `.item()` per image,
+        DGFRCNN.py:165,177,193), so the untouched heads keep `.grad is None` and the optimizer skips them exactly as
+        it does for the reference.  Returns the mean over the kept terms (DGFRCNN.py:170,181,196)."""
         feats = self.box_features                                           # [B*S, 1024]
         B = len(self.box_labels)
         labels = torch.stack(self.box_labels).reshape(-1)                   # [B*S]
         S = labels.numel() // B
+        D = len(heads)
+        if dom_list is None:
+            used = list(range(D))
+        elif own_domain:
+            used = sorted(set(dom_list))
+        else:
+            used = [j for j in range(D) if any(d != j for d in dom_list)]
         per = []
-        for head in heads:
-            ce = F.cross_entropy(head(feats), labels, reduction="none").view(B, S).mean(1)
-            per.append(ce)
+        for j in used:
+            ce = F.cross_entropy(heads[j](feats), labels, reduction="none").view(B, S)
+            n = (labels.view(B, S) >= 0).sum(1).clamp(min=1)                # == S unless the sampler left slots empty
+            per.append(ce.sum(1) / n)
+        if dom_list is not None:
+            # the kept (image, head) terms in the reference loop's order; views + one stack, no host->device traffic
+            terms = [per[k][i] for i, d in enumerate(dom_list) for k, j in enumerate(used) if (j == d) == own_domain]
+            return torch.stack(terms).mean()
         per = torch.stack(per, dim=1)                                       # [B, D]
-        own = F.one_hot(domain.long(), len(heads)).to(per.dtype)
+        own = F.one_hot(domain.long(), D).to(per.dtype)
         keep = own if own_domain else 1.0 - own
         return (per * keep).sum() / keep.sum()
 
@@ -151,7 +173,10 @@ class DGFRCNN(nn.Module):
         imgs, boxes, labels, domain = batch
         dev = imgs[0].device
         targets = [{"boxes": b.float(), "labels": l.long()} for b, l in zip(boxes, labels)]
-        domain = domain.to(dev)
+        # batch[3] is a host tensor in the reference (DGcommon.collate_fn; `.to(device=0)` at DGFRCNN.py:150): reading
+        # the ids there costs nothing.  A device tensor works too, at the price of one device->host read in modes 2-4.
+        dom_host = domain.tolist() if (self.mode >= 2 and (not domain.is_cuda or not self.batched_modes or self.exact_head_set)) else None
+        domain = domain.to(dev, non_blocking=True)
         if self.batched_modes and self.mode >= 2:
             if self.mode == 2:
                 for head in self.InsCls:
@@ -159,20 +184,20 @@ class DGFRCNN(nn.Module):
                         p.requires_grad = True
                 with torch.no_grad():
                     self.detector(imgs, targets)
-                loss = self.reg_weights[4] * self._instance_losses_batched(self.InsCls, domain, True)
+                loss = self.reg_weights[4] * self._instance_losses_batched(self.InsCls, domain, True, dom_host)
             elif self.mode == 3:
                 self.detector(imgs, targets)
-                loss = self.reg_weights[3] * self._instance_losses_batched(self.InsClsPrime, domain, True)
+                loss = self.reg_weights[3] * self._instance_losses_batched(self.InsClsPrime, domain, True, dom_host)
             else:
                 for head in self.InsCls:
                     for p in head.parameters():
                         p.requires_grad = False
                 self.detector(imgs, targets)
-                loss = self.reg_weights[4] * self._instance_losses_batched(self.InsCls, domain, False)
+                loss = self.reg_weights[4] * self._instance_losses_batched(self.InsCls, domain, False, dom_host)
                 self.sub_mode = 0
             self.mode = 0
             return loss
-        dom_list = domain.tolist() if self.mode >= 2 else None
+        dom_list = dom_host
         if self.mode == 0:
             det = self.detector(imgs, targets)
             loss = sum(v for d in det for v in d["losses"].values())      # DGFRCNN.py:126-127
@@ -226,21 +251,4 @@ class DGFRCNN(nn.Module):
         return loss
 
 
-def allreduce_gradients(params, world_size: int) -> None:
-    """Data-parallel gradient average over the ranks as ONE flat NCCL all-reduce.
-    The 5-mode schedule leaves different parameter subsets without gradients on different steps
-    (DGFRCNN.py:164-167,189); the mode is identical on all ranks, so the set of parameters that
-    have a gradient is consistent and no unused-parameter bookkeeping is needed."""
-    if world_size <= 1:
-        return
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
-        return
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    flat.div_(world_size)
-    off = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
-        off += n
+from .ddp import GradSync, allreduce_gradients  # noqa: E402,F401  (data-parallel gradient sync lives in ddp.py)

@@ -594,7 +594,7 @@ def _msroi_bwd_op(grad: Tensor, rois: Tensor, roi_img_offsets: Optional[Tensor],
     lib = _lib.load()
     n_levels = len(scales)
     b, c = shapes[0], shapes[1]
-    if not channels_last and not aligned and algo in (0, 3) and _tma_shape(c, pooled_h, pooled_w, sampling_ratio):
+    if not channels_last and not aligned and algo in (0, 3, 4) and _tma_shape(c, pooled_h, pooled_w, sampling_ratio):
         channels_last = True     # gradients of NCHW maps are returned in channels_last memory (same values)
     mf = torch.channels_last if channels_last else torch.contiguous_format
     grads = [torch.empty((b, c, shapes[2 + 2 * l], shapes[3 + 2 * l]), dtype=grad.dtype, device=grad.device,
@@ -608,7 +608,7 @@ def _msroi_bwd_op(grad: Tensor, rois: Tensor, roi_img_offsets: Optional[Tensor],
     ptrs, keep_alive = _level_ptrs(grads)
     esz = grad.element_size()
     tok = KernelTimer.start("msroi_align_bwd", n * c * pooled_h * pooled_w * esz + 20 * n + sum(g.numel() for g in grads) * esz)
-    wsb = lib.dgod_msroi_align_bwd_workspace_bytes(n)
+    wsb = lib.dgod_msroi_align_bwd_workspace_bytes_cfg(C.byref(cfg), n)
     ws = _ws(wsb, grad.device)
     check(lib.dgod_msroi_align_bwd(C.byref(cfg), _p(grad), _p(rois), n, _p(roi_img_offsets), ptrs, int(algo),
                                    _p(ws), wsb, _stream()))

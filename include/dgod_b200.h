@@ -42,7 +42,7 @@ extern "C" {
 
 typedef void* dgod_stream_t; /* a cudaStream_t (0 = legacy default stream) */
 
-#define DGOD_ABI_VERSION 1
+#define DGOD_ABI_VERSION 2
 
 enum {
   DGOD_OK = 0,
@@ -223,17 +223,22 @@ int dgod_msroi_align_fwd(const dgod_roi_config* cfg /*host*/,
                          const float* rois, int n_rois, void* out,
                          void* workspace, size_t workspace_bytes, dgod_stream_t stream);
 size_t dgod_msroi_align_bwd_workspace_bytes(int n_rois);
+/* Workspace for the configuration at hand (>= the size above): additionally holds the per-tile RoI lists of the
+ * owner-computes kernel, whose size depends on the level geometry. */
+size_t dgod_msroi_align_bwd_workspace_bytes_cfg(const dgod_roi_config* cfg /*host*/, int n_rois);
 /* grad_feats[l] is fully overwritten (zero where no RoI contributes): no memset required.
- * algo 0 picks the TMA bulk-reduce kernel when the shape allows (channels_last, 7x7 bins,
- * sampling_ratio 1..2, C in {64,128,256}, cooperative launch), else the vector-RED / atomic scatter (fp32) or
- * the deterministic tile gather (bf16); 1 forces the scatter, 2 the tile gather, 3 the TMA kernel.
- * workspace: dgod_msroi_align_bwd_workspace_bytes(n_rois) bytes, 128-byte aligned (RoI plans, counters). */
+ * algo 0 picks the owner-computes kernel when the shape allows (channels_last, 7x7 bins, sampling_ratio 1..2,
+ * C % 64 == 0) and the workspace has dgod_msroi_align_bwd_workspace_bytes_cfg bytes: every tile of the gradient
+ * maps is accumulated on chip and written once, deterministic.  Else the TMA bulk-reduce kernel (C in
+ * {64,128,256}, cooperative launch), else the vector-RED / atomic scatter (fp32) or the deterministic tile
+ * gather (bf16); 1 forces the scatter, 2 the tile gather, 3 the TMA bulk-reduce kernel, 4 owner-computes.
+ * workspace: 128-byte aligned (RoI plans, tile lists, counters). */
 int dgod_msroi_align_bwd(const dgod_roi_config* cfg /*host*/,
                          const void* grad_out /*device [K,C,PH,PW]*/,
                          const float* rois, int n_rois,
                          const int32_t* roi_img_offsets /*device [batch+1] or NULL*/,
                          void* const* grad_feats /*host array of device ptrs*/,
-                         int algo /*0 auto, 1 scatter, 2 tile gather, 3 TMA bulk reduce*/,
+                         int algo /*0 auto, 1 scatter, 2 tile gather, 3 TMA bulk reduce, 4 owner-computes*/,
                          void* workspace, size_t workspace_bytes, dgod_stream_t stream);
 
 /* ------------------------------------------------------------------ box head post-processing */

@@ -146,6 +146,21 @@ def gen_hotpath(fasterrcnn):
     model.train()
     images = ImageList(torch.zeros(HOT["batch"], 3, h, w), [(h, w)] * HOT["batch"])
     torch.manual_seed(1234)
+    # the samplers draw from torch's global RNG: record what they picked so that the GPU mirror can be given the
+    # same selection (detector.BalancedSampler `keys`) and everything downstream compared value for value
+    picks = {"rpn": [], "roi": []}
+
+    def recording(sampler, key):
+        call = sampler.__call__
+
+        def wrapped(matched_idxs):
+            pos, neg = call(matched_idxs)
+            picks[key].append((torch.stack(pos), torch.stack(neg)))
+            return pos, neg
+        return wrapped
+
+    model.rpn.fg_bg_sampler = recording(model.rpn.fg_bg_sampler, "rpn")
+    model.roi_heads.fg_bg_sampler = recording(model.roi_heads.fg_bg_sampler, "roi")
     proposals, rpn_losses = model.rpn(images, features, targets)
     anchors = model.rpn.anchor_generator(images, list(features.values()))
     labels, _ = model.rpn.assign_targets_to_anchors(anchors, targets)
@@ -158,6 +173,10 @@ def gen_hotpath(fasterrcnn):
         anchor_labels=torch.stack(labels).numpy().astype(np.int8),
         roi_labels=torch.stack(grabbed["labels"]).numpy(),
         pooled_sum=grabbed["pooled"].detach().double().sum(dim=(1, 2, 3)).numpy(),
+        rpn_pos=np.packbits(torch.cat([p for p, _ in picks["rpn"]]).numpy().astype(np.uint8), axis=1),
+        rpn_neg=np.packbits(torch.cat([n for _, n in picks["rpn"]]).numpy().astype(np.uint8), axis=1),
+        roi_pos=np.packbits(torch.cat([p for p, _ in picks["roi"]]).numpy().astype(np.uint8), axis=1),
+        roi_neg=np.packbits(torch.cat([n for _, n in picks["roi"]]).numpy().astype(np.uint8), axis=1),
         loss_objectness=rpn_losses["loss_objectness"].detach().numpy(),
         loss_rpn_box_reg=rpn_losses["loss_rpn_box_reg"].detach().numpy(),
         loss_classifier=roi_losses["loss_classifier"].detach().numpy(),

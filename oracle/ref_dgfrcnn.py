@@ -87,8 +87,8 @@ class RefFasterRCNN(GeneralizedRCNN):
     """fasterrcnn.py:354-499 + factory :307-329 with pretrained=False."""
 
     def __init__(self, num_classes=9, min_size=800, max_size=1333, box_batch_size_per_image=512,
-                 rpn_batch_size_per_image=256):
-        backbone = resnet_fpn_backbone(backbone_name="resnet50", weights=None, trainable_layers=5)
+                 rpn_batch_size_per_image=256, trainable_layers=5):
+        backbone = resnet_fpn_backbone(backbone_name="resnet50", weights=None, trainable_layers=trainable_layers)
         oc = backbone.out_channels
         ag = AnchorGenerator(((32,), (64,), (128,), (256,), (512,)), ((0.5, 1.0, 2.0),) * 5)
         rpn = PerImageRPN(ag, RPNHead(oc, ag.num_anchors_per_location()[0]), 0.7, 0.3, rpn_batch_size_per_image, 0.5,
@@ -169,7 +169,9 @@ class RefDGFRCNN(nn.Module):
         self.InsDA = _InstanceHead(num_domains, True)
         self.InsClsPrime = nn.ModuleList([_InstanceHead(n_classes, True) for _ in range(num_domains)])
         self.InsCls = nn.ModuleList([_InstanceHead(n_classes, False) for _ in range(num_domains)])
-        self.detector = RefFasterRCNN(n_classes, min_size, max_size)
+        # DGFRCNN.py:81: fasterrcnn_resnet50_fpn(num_classes=n_classes, pretrained=True, trainable_backbone_layers=3)
+        # -> FastRCNNPredictor(in_features, n_classes + 1) (fasterrcnn.py:327), conv1 / layer1 frozen (fasterrcnn.py:317)
+        self.detector = RefFasterRCNN(n_classes + 1, min_size, max_size, trainable_layers=3)
         self.ImageDA = _ImageHead(num_domains)
         self.detector.backbone.register_forward_hook(lambda m, i, o: setattr(self, "base_feat", o))
         self.detector.roi_heads.box_head.register_forward_hook(self._grab)

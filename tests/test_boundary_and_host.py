@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/dgod_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == names, "dgod_b200/_lib.py and the header disagree"
     loaded = _lib.load()
-    assert loaded.dgod_abi_version() == 1
+    assert loaded.dgod_abi_version() == _lib.ABI_VERSION
     assert loaded.dgod_last_error() is not None
 
 

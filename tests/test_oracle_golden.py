@@ -143,9 +143,10 @@ def test_fixtures_are_current():
             G.gen_fcos_step(fcos)
             G.gen_fcos_loss(fcos)
             G.gen_hotpath(fasterrcnn)
+            G.gen_step(fasterrcnn)
         finally:
             G.OUT = old
-        for name in ("fcos_assign.npz", "fcos_step.npz", "fcos_loss.npz", "frcnn_hotpath.npz"):
+        for name in ("fcos_assign.npz", "fcos_step.npz", "fcos_loss.npz", "frcnn_hotpath.npz", "frcnn_step.npz"):
             a, b = np.load(Path(d) / name), np.load(GOLD / name)
             for k in b.files:
                 assert np.array_equal(a[k], b[k]), (name, k)

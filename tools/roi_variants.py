@@ -17,12 +17,13 @@ def build(specs):
     for spec in specs:
         tag, _, flags = spec.partition(":")
         flags = [f for f in flags.split(",") if f]
-        src = B.CSRC / "roi_align_tma.cu"
+        src_name = os.environ.get("VARIANT_SRC", "roi_align_tma.cu")     # which .cu the -D flags apply to
+        src = B.CSRC / src_name
         if "@" in tag:
             tag, rev = tag.split("@")
             src = B.CSRC / f"_ref_{tag}.cu"
             src.write_text(subprocess.check_output(["git", "show", f"{rev}:dgod_b200/csrc/roi_align_tma.cu"], text=True))
-        obj = VAR / f"roi_align_tma_{tag}.o"
+        obj = VAR / f"{Path(src_name).stem}_{tag}.o"
         cmd = [B._nvcc(), *B.NVCC_FLAGS, *flags, "-c", str(src), "-o", str(obj)]
         procs.append((tag, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
     for tag, obj, p in procs:
@@ -33,7 +34,7 @@ def build(specs):
         names = [l for l in err.splitlines() if "Function properties" in l]
         for n, r in zip(names, regs):
             if "IfLi256ELi2" in n and "tma" in n: print(tag, n.split("_ZN4dgod")[1][:24], r.split(":")[1].strip()[:60])
-        objs = [str(obj if s == "roi_align_tma.cu" else B.OBJ_DIR / (Path(s).stem + ".o")) for s in B.SOURCES]
+        objs = [str(obj if s == src_name else B.OBJ_DIR / (Path(s).stem + ".o")) for s in B.SOURCES]
         subprocess.check_call([B._nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(VAR / f"lib_{tag}.so"), *objs])
         print("built", tag)
 
@@ -56,7 +57,7 @@ def run_one(tag, dtype_name="f32", per=512, iters=15):
     grads = [torch.empty_like(f) for f in feats]
     cfg, _ = ops._roi_config(feats, [1/4, 1/8, 1/16, 1/32], 7, 7, 2, False, 2, 5, 224.0, 4.0)
     cfg.channels_last = 1
-    wsb = max(lib.dgod_msroi_align_bwd_workspace_bytes(K), lib.dgod_msroi_align_fwd_workspace_bytes(K))
+    wsb = max(lib.dgod_msroi_align_bwd_workspace_bytes_cfg(C.byref(cfg), K), lib.dgod_msroi_align_fwd_workspace_bytes(K))
     ws = torch.zeros(wsb, dtype=torch.uint8, device=DEV)
     fptrs, keep1 = ops._level_ptrs(feats)
     gptrs, keep2 = ops._level_ptrs(grads)
