@@ -18,9 +18,13 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
-// Waits with a suspend-time hint (as CUTLASS's ClusterBarrier::wait does): the thread sleeps until the phase
-// completes instead of spinning on try_wait.
+// Spin on try_wait (no suspend-time hint: with a hint ptxas emits a NANOSLEEP back-off loop whose wake-up
+// granularity adds ~1 us to every wait that actually blocks — measured on the owner-computes backward's ring).
+#ifndef DGOD_MBAR_WAIT_HINT
+#define DGOD_MBAR_WAIT_HINT 0
+#endif
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+#if DGOD_MBAR_WAIT_HINT
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -30,6 +34,29 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+#else
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
+}
+// Pure polling (test_wait never suspends the thread): for waits on the critical path of a producer/consumer ring.
+__device__ __forceinline__ void mbar_spin(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SPIN_%=:\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra SDONE_%=;\n"
+      "bra SPIN_%=;\n"
+      "SDONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 // global -> shared bulk copy, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {

@@ -15,27 +15,37 @@
 // Three kernels:
 //   own_plan_kernel  one warp per RoI: level mapping, sampling taps (axis_tap(), i.e. TV's out-of-range
 //                    skip and border clamp), the ascending lists of live feature rows / columns (<= 28
-//                    each however large the RoI is) and the separable weight tables A_y[row][ph]/count,
-//                    A_x[col][pw] -> a 1 920-byte plan; plus a 16-byte record (level, image, footprint box).
+//                    each however large the RoI is), the separable weight tables A_y[row][ph]/count and
+//                    A_x[col][pw], and the BLOCKED form of A_x: absolute 4-column blocks, each with a base
+//                    bin such that all its weights sit on 4 consecutive bins (3 of 4 RoIs have one) ->
+//                    a 2 560-byte plan; plus a 16-byte record (level, image, footprint box).
 //   own_bin_kernel   one warp per tile: the RoIs (index order) whose footprint box meets the tile.
-//   own_bwd_kernel   persistent, one CTA per SM.  A producer warp streams (plan, [64][49] gradient slice)
-//                    pairs through a ring of stages with cp.async.bulk + mbarrier complete_tx, one lane per
-//                    stage; 16 consumer warps are decoupled from each other (they own disjoint
-//                    accumulators) and meet only at the per-stage empty barrier.  Per RoI and warp:
-//                        T[pw]       = sum_ph A_y[row][ph] * g[ph][pw]        (rows of this warp, zero ph skipped)
-//                        acc[row][x] += sum_pw A_x[x][pw] * T[pw]             (live columns of the tile)
-//                    with packed FFMA2 on the lane's channel pair.
+//   own_bwd_kernel   persistent, one CTA per SM, 16 warps, work items (tile x 64-channel slice) dealt
+//                    round-robin with the coarse levels first.  Warp roles:
+//                      producer  lane 0 streams (plan, [64][49] gradient slice) pairs through a ring of 15
+//                                stages with two tensor-map loads per stage (cp.async.bulk.tensor, SASS
+//                                UTMALDG; completion counted in bytes on the stage's `full` mbarrier);
+//                      decoder   once per pair (not once per consumer warp) intersects the RoI's live
+//                                rows / columns with the tile and publishes masks, list offsets and the
+//                                tile's 4 block descriptors in shared memory (`ready` mbarrier); for a plan
+//                                without a blocked form it tries to build one for this tile;
+//                      14 consumers, decoupled from each other (they own disjoint accumulators), meet only
+//                                at the per-stage `empty` barrier.  Per pair and warp:
+//                                  T[pw]       = sum_ph A_y[row][ph] * g[ph][pw]   (zero bins skipped)
+//                                  acc[row][x] += sum_pw A_x[x][pw] * T[pw]
+//                                the second line per block of 4 columns x 4 bins, branch-free, packed FFMA2
+//                                on the lane's channel pair (general form: 7 bins per live column).
 //
-// Roofline: HBM.  Algorithmic bytes K*C*49*s + 20K + sum_l B*C*H_l*W_l*s.  On chip the
-// gradient slices are re-read once per tile an RoI meets (about 3 at this tile size) from the L2.
+// Roofline: HBM.  Algorithmic bytes K*C*49*s + 20K + sum_l B*C*H_l*W_l*s; measured DRAM
+// traffic 0.98x of that (profiles/).  On chip the gradient slices are re-read once per tile an RoI meets
+// (2.8 at this tile size) from the L2.  What bounds the kernel today is instruction issue in the consumer
+// warps (profiles/README.md has the ablation: ring + decode 40 %, T 10 %, block sweeps 35 %, stores 15 %).
+// Compile-time switches for those ablations: DGOD_OWN_SKIP_T / _SKIP_COLS / _SKIP_STORE, DGOD_OWN_TIMING.
 #include <algorithm>
 #include "roi_common.cuh"
 #include "bulk.cuh"
 #include "tmap.cuh"
 
-#ifndef DGOD_OWN_TMAP
-#define DGOD_OWN_TMAP 1   // 1: one elected lane issues tensor-map loads (UTMALDG); 0: one lane per stage issues 1-D bulk copies
-#endif
 
 namespace dgod {
 
@@ -45,26 +55,52 @@ constexpr int kP = 7;                  // pooled size (PH = PW = 7)
 constexpr int kNB = kP * kP;
 constexpr int kMaxSamp = 14;           // samples per axis (kP * sampling_ratio, sr <= 2)
 constexpr int kMaxLive = 2 * kMaxSamp; // live rows / columns per axis
-constexpr int kTileH = 28, kTileW = 16;   // 14 consumer warps + the producer warp = 15 warps: 128 registers per thread
+constexpr int kTileH = 28, kTileW = 16;
 constexpr int kCS = 64;                // channels per slice: lane c owns c and c + 32
-constexpr int kWarps = kTileH / 2;     // consumer warps, two adjacent tile rows each
-constexpr int kThreads = kWarps * 32 + 32;
-constexpr int kCounterBytes = 8192;   // [0] pair cursor; +1024: per-CTA cycle counters of DGOD_OWN_TIMING builds
+#define OWN_WAIT mbar_wait
+#ifndef DGOD_OWN_RPW
+#define DGOD_OWN_RPW 2
+#endif
+constexpr int kRPW = DGOD_OWN_RPW;     // tile rows per consumer warp: 1 -> 28 consumer warps of <= 64 registers, 2 -> 14 of <= 128
+constexpr int kWarps = kTileH / kRPW;  // consumer warps; + the producer warp + the decoder warp
+constexpr int kThreads = (kWarps + 2) * 32;
+constexpr int kBlk = 4;                // the consumers sweep a tile row in blocks of 4 columns (absolute columns 4m .. 4m+3) ...
+constexpr int kTaps = 4;               // ... whose weights sit on 4 consecutive bins (else the general 7-bin form runs)
+constexpr int kMaxBlk = 8;             // blocks a span of <= 28 columns can meet
+constexpr int kOwnTable = 0x40000000;  // PairInfo::w_off: the weights are in PairInfo::wtab, not in the plan
+constexpr int kCounterBytes = 73728;   // [0] pair cursor; +1024: per-CTA, per-warp cycle counters of DGOD_OWN_TIMING builds
 
 struct alignas(128) Plan {
   short n_rows, n_cols;                // 16-byte header, read by the consumers as one int4
   short y_first, y_last;               // extent of the live rows
   short x_first, x_last;               // extent of the live columns
-  short span_mode, pad;                // 1: cols[] are the consecutive columns x_first .. x_last (<= 28 of them)
+  short blocked;                       // 1: span mode (consecutive columns) and every block fits kTaps bins: wblk / blk are valid
+  short pad0;
   short rows[kMaxLive];                // live feature rows, ascending (padding 0x7fff)
   short cols[kMaxLive];                // live feature columns, ascending (span mode: every column of the span)
   float ay[kMaxLive][8];               // A_y[row][ph] / count, list order
-  float ax[kMaxLive][8];               // A_x[col][pw], list order (zero rows for columns without weight)
+  float ax[kMaxLive][8];               // A_x[col][pw], list order (zero rows for columns without weight): the general form
+  float4 wblk[kMaxBlk][kBlk];          // blocked form: weights of bins pb0 .. pb0+3 of absolute column 4*(x_first/4 + b) + c, zeros outside
+  unsigned char blk[kMaxBlk];          // bits 0-1: pb0 of block b; bit 2: the block has a column with weight
+  unsigned char aymask[kMaxLive];      // bit ph: A_y[row][ph] != 0
+  unsigned char pad[92];
 };
-static_assert(sizeof(Plan) == 1920, "plans are moved with bulk copies");
+static_assert(sizeof(Plan) == 2560, "plans are moved with tensor-map loads");
 
 struct alignas(16) Bin { int level, batch; short y0, y1, x0, x1; };   // level < 0: nothing to add
 static_assert(sizeof(Bin) == 16, "read as one int4");
+
+// What the decoder warp hands the consumer warps for one (RoI, tile) pair, so that the intersection of the RoI's live rows /
+// columns with the tile is computed once per pair instead of once per consumer warp.
+struct alignas(16) PairInfo {
+  unsigned rowmask;                    // bit r: tile row r is live
+  unsigned i_first;                    // list index of the first live row inside the tile
+  unsigned blocks;                     // blocked form: byte B = block B of the tile (bits 0-1 base bin, bit 2 has weight); bit 31: general form
+  int w_off;                           // blocked form: first wblk entry of the tile's block 0 (may be negative)
+  unsigned colmask, j_first, pad0, pad1;   // general form: live tile columns, list index of the first one
+  float4 wtab[kTileW];                 // blocked form of an RoI whose plan has none (w_off == kOwnTable): built per tile by the decoder
+};
+static_assert(sizeof(PairInfo) == 32 + 16 * kTileW, "16-byte reads");
 
 struct Tiles {
   int n_levels, n_slices, n_tiles, B;
@@ -168,11 +204,55 @@ own_plan_kernel(const RoiDev g, const float* __restrict__ rois, int n_rois, Plan
   const int span = x_last - x_first + 1;
   const int span_mode = n_rows && span <= kMaxLive;
   const int n_cols_out = span_mode ? span : n_cols;
+  // A_x, one lane per table row; in span mode also the blocked form: absolute 4-column blocks, each with a base bin pb0
+  // such that every weight of its columns sits on bins pb0 .. pb0+3 (if one block needs more, the RoI keeps the general form)
+  bool wide = false;
+  if (n_rows) {
+    float wv[8];
+    const int col = span_mode ? x_first + lane : (int)t.list[1][lane < n_cols ? lane : 0];
+    const bool in_list = lane < n_cols_out;
+    unsigned nz = 0;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      wv[p] = (in_list && lane < kMaxLive && p < kP) ? axis_weight(t.lo[1], t.hi[1], t.l[1], t.h[1], col, p, sr) : 0.f;
+      if (wv[p] != 0.f) nz |= 1u << p;
+    }
+    if (lane < kMaxLive) {
+      *reinterpret_cast<float4*>(&P.ax[lane][0]) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+      *reinterpret_cast<float4*>(&P.ax[lane][4]) = make_float4(wv[4], wv[5], wv[6], wv[7]);
+    }
+    P.wblk[lane >> 2][lane & 3] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < kMaxBlk) P.blk[lane] = 0;
+    __syncwarp();
+    if (span_mode) {
+      const int c = col & 3, bi = (col >> 2) - (x_first >> 2);
+      int lo = nz ? __ffs(nz) - 1 : kP, hi = nz ? 31 - __clz(nz) : -1;
+      int blo = kP, bhi = -1;
+#pragma unroll
+      for (int d = 0; d < kBlk; ++d) {                       // the (up to 4) lanes of this lane's block
+        const int src = lane - c + d;
+        const int olo = __shfl_sync(0xffffffffu, lo, src & 31), ohi = __shfl_sync(0xffffffffu, hi, src & 31);
+        if (src >= 0 && src < n_cols_out) { blo = min(blo, olo); bhi = max(bhi, ohi); }
+      }
+      const int pb0 = min(blo, kP - kTaps);
+      wide = in_list && bhi > pb0 + kTaps - 1;
+      if (in_list) {
+        float4 e;
+        e.x = pb0 == 0 ? wv[0] : pb0 == 1 ? wv[1] : pb0 == 2 ? wv[2] : wv[3];
+        e.y = pb0 == 0 ? wv[1] : pb0 == 1 ? wv[2] : pb0 == 2 ? wv[3] : wv[4];
+        e.z = pb0 == 0 ? wv[2] : pb0 == 1 ? wv[3] : pb0 == 2 ? wv[4] : wv[5];
+        e.w = pb0 == 0 ? wv[3] : pb0 == 1 ? wv[4] : pb0 == 2 ? wv[5] : wv[6];
+        P.wblk[bi][c] = e;
+        if (c == 0 || lane == 0) P.blk[bi] = (unsigned char)((pb0 & 3) | (bhi >= 0 ? 4 : 0));
+      }
+    }
+  }
+  const int blocked = span_mode && !__any_sync(0xffffffffu, wide);
   if (lane == 0) {
     P.n_rows = (short)n_rows; P.n_cols = (short)n_cols_out;
     P.y_first = n_rows ? t.list[0][0] : (short)0; P.y_last = n_rows ? t.list[0][n_rows - 1] : (short)-1;
     P.x_first = (short)x_first; P.x_last = (short)x_last;
-    P.span_mode = (short)span_mode; P.pad = 0;
+    P.blocked = (short)blocked; P.pad0 = 0;
     Bin b;
     b.level = n_rows ? r.level : -1;
     b.batch = usable ? r.batch : -1;
@@ -183,13 +263,17 @@ own_plan_kernel(const RoiDev g, const float* __restrict__ rois, int n_rois, Plan
   if (lane < kMaxLive) {
     P.rows[lane] = lane < n_rows ? t.list[0][lane] : (short)0x7fff;
     P.cols[lane] = lane < n_cols_out ? (span_mode ? (short)(x_first + lane) : t.list[1][lane]) : (short)0x7fff;
-  }
-  const float inv = 1.f / r.count;             // count = sr*sr: a power of two, so scaling the table is exact
-  for (int e = lane; e < kMaxLive * 8; e += 32) {
-    const int i = e >> 3, p = e & 7;
-    P.ay[i][p] = (i < n_rows && p < kP) ? axis_weight(t.lo[0], t.hi[0], t.l[0], t.h[0], t.list[0][i], p, sr) * inv : 0.f;
-    const int col = span_mode ? x_first + i : (int)t.list[1][i < n_cols ? i : 0];
-    P.ax[i][p] = (i < n_cols_out && p < kP) ? axis_weight(t.lo[1], t.hi[1], t.l[1], t.h[1], col, p, sr) : 0.f;
+    const float inv = 1.f / r.count;           // count = sr*sr: a power of two, so scaling the table is exact
+    unsigned m = 0;
+    float wv[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      wv[p] = (lane < n_rows && p < kP) ? axis_weight(t.lo[0], t.hi[0], t.l[0], t.h[0], t.list[0][lane], p, sr) * inv : 0.f;
+      if (wv[p] != 0.f) m |= 1u << p;
+    }
+    *reinterpret_cast<float4*>(&P.ay[lane][0]) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+    *reinterpret_cast<float4*>(&P.ay[lane][4]) = make_float4(wv[4], wv[5], wv[6], wv[7]);
+    P.aymask[lane] = (unsigned char)m;
   }
 }
 
@@ -238,7 +322,7 @@ template <typename T> struct Cfg {
   static constexpr int kSmem = kStages * kStageBytes;
   // the tensor maps see grad_out / the plans as rows of 32-bit words
   static constexpr int kGRowWords = 196, kGBoxRows = kGBytes / (kGRowWords * 4);       // [64][49] slice = 16 (fp32) / 8 (bf16) rows
-  static constexpr int kPlanRowWords = 240, kPlanBoxRows = (int)sizeof(Plan) / (kPlanRowWords * 4);
+  static constexpr int kPlanRowWords = 128, kPlanBoxRows = (int)sizeof(Plan) / (kPlanRowWords * 4);
   static_assert(kGBoxRows * kGRowWords * 4 == kGBytes && kPlanBoxRows * kPlanRowWords * 4 == (int)sizeof(Plan), "box shapes");
   static_assert(kStageBytes % 128 == 0 && kStages >= 4 && kStages <= 32, "stage ring");
 };
@@ -249,65 +333,107 @@ template <> __device__ __forceinline__ float lds_as_f32<__nv_bfloat16>(const __n
   return __uint_as_float((unsigned)(*reinterpret_cast<const unsigned short*>(p)) << 16);
 }
 
-// acc{0,1}[x] += sum_pw w[pw] * t{0,1}[pw] for the two rows of this warp (packed pairs of channels)
-__device__ __forceinline__ void column_update(const float4 w0, const float4 w1, const float2 (&t0)[kP], const float2 (&t1)[kP],
-                                              float2& a0, float2& a1) {
-  a0 = __ffma2_rn(make_float2(w0.x, w0.x), t0[0], a0); a1 = __ffma2_rn(make_float2(w0.x, w0.x), t1[0], a1);
-  a0 = __ffma2_rn(make_float2(w0.y, w0.y), t0[1], a0); a1 = __ffma2_rn(make_float2(w0.y, w0.y), t1[1], a1);
-  a0 = __ffma2_rn(make_float2(w0.z, w0.z), t0[2], a0); a1 = __ffma2_rn(make_float2(w0.z, w0.z), t1[2], a1);
-  a0 = __ffma2_rn(make_float2(w0.w, w0.w), t0[3], a0); a1 = __ffma2_rn(make_float2(w0.w, w0.w), t1[3], a1);
-  a0 = __ffma2_rn(make_float2(w1.x, w1.x), t0[4], a0); a1 = __ffma2_rn(make_float2(w1.x, w1.x), t1[4], a1);
-  a0 = __ffma2_rn(make_float2(w1.y, w1.y), t0[5], a0); a1 = __ffma2_rn(make_float2(w1.y, w1.y), t1[5], a1);
-  a0 = __ffma2_rn(make_float2(w1.z, w1.z), t0[6], a0); a1 = __ffma2_rn(make_float2(w1.z, w1.z), t1[6], a1);
+// acc[r] += sum_pw w[pw] * t[r][pw]: all 7 bins (the general form)
+__device__ __forceinline__ void column_dense(const float4 w0, const float4 w1, const float2 (&t)[kRPW][kP], float2 (&acc)[kRPW][kTileW],
+                                             int x) {
+  const float w[kP] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z};
+#pragma unroll
+  for (int pw = 0; pw < kP; ++pw)
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r) acc[r][x] = __ffma2_rn(make_float2(w[pw], w[pw]), t[r][pw], acc[r][x]);
+}
+
+// One block of 4 tile columns whose weights sit on bins P0 .. P0+3 (the plan's wblk row): 4 broadcast reads, then
+// 4 columns x kRPW rows x 4 multiply-adds with no branch and no dependence between columns.
+template <int B, int P0>
+__device__ __forceinline__ void column_block(const float4* __restrict__ wtab, const float2 (&t)[kRPW][kP], float2 (&acc)[kRPW][kTileW]) {
+  float4 w[kBlk];
+#pragma unroll
+  for (int c = 0; c < kBlk; ++c) w[c] = wtab[c];
+#pragma unroll
+  for (int c = 0; c < kBlk; ++c)
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r) acc[r][B * kBlk + c] = __ffma2_rn(make_float2(w[c].x, w[c].x), t[r][P0], acc[r][B * kBlk + c]);
+#pragma unroll
+  for (int c = 0; c < kBlk; ++c)
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r) acc[r][B * kBlk + c] = __ffma2_rn(make_float2(w[c].y, w[c].y), t[r][P0 + 1], acc[r][B * kBlk + c]);
+#pragma unroll
+  for (int c = 0; c < kBlk; ++c)
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r) acc[r][B * kBlk + c] = __ffma2_rn(make_float2(w[c].z, w[c].z), t[r][P0 + 2], acc[r][B * kBlk + c]);
+#pragma unroll
+  for (int c = 0; c < kBlk; ++c)
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r) acc[r][B * kBlk + c] = __ffma2_rn(make_float2(w[c].w, w[c].w), t[r][P0 + 3], acc[r][B * kBlk + c]);
+}
+
+// `blocks`: byte B describes the tile's block B (bits 0-1: base bin, bit 2: has weight); `w`: its 4 table entries
+template <int B>
+__device__ __forceinline__ void column_block_any(unsigned blocks, const float4* __restrict__ w, const float2 (&t)[kRPW][kP],
+                                                 float2 (&acc)[kRPW][kTileW]) {
+  if ((blocks >> (8 * B + 2)) & 1u) {
+    const unsigned p0 = (blocks >> (8 * B)) & 3u;
+    if (p0 == 0) column_block<B, 0>(w + B * kBlk, t, acc);
+    else if (p0 == 1) column_block<B, 1>(w + B * kBlk, t, acc);
+    else if (p0 == 2) column_block<B, 2>(w + B * kBlk, t, acc);
+    else column_block<B, 3>(w + B * kBlk, t, acc);
+  }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1)
 own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorMap tm_plan, const __grid_constant__ CUtensorMap tm_g,
-               const Plan* __restrict__ plans, const T* __restrict__ grad_out, const int2* __restrict__ tile_list,
-               const int* __restrict__ pair_k, long long* __restrict__ timing) {
+               const int2* __restrict__ tile_list, const int* __restrict__ pair_k, long long* __restrict__ timing) {
   constexpr int NS = Cfg<T>::kStages;
   constexpr int SB = Cfg<T>::kStageBytes;
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ alignas(8) unsigned long long full[NS], empty[NS];
+  __shared__ alignas(8) unsigned long long full[NS], ready[NS], empty[NS];
+  __shared__ PairInfo info[NS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_items = tg.n_tiles * tg.n_slices;
+
   const int C = g.C;
 
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
       mbar_init(&full[i], 1);
+      mbar_init(&ready[i], 1);
       mbar_init(&empty[i], kWarps);
     }
     mbar_fence_init();
-#if DGOD_OWN_TMAP
     tmap_prefetch(&tm_plan);
     tmap_prefetch(&tm_g);
-#endif
   }
   __syncthreads();
 
   if (warp == kWarps) {
-#if DGOD_OWN_TMAP
-    // ------------------------------------------------------------------ producer: the warp walks the pair lists together
-    // (32 RoI indices per coalesced read, the next item's first chunk prefetched); lane 0 issues the two tensor-map
-    // loads of a stage in order, as far ahead as the ring allows.
+    // ------------------------------------------------------------------ producer.  Walks the pair lists of this CTA's
+    // items (tile x channel slice, dealt round-robin: heavy levels first) with the whole warp — 32 RoI indices per coalesced
+    // read, the next item's first chunk read early; lane 0 issues the two tensor-map loads of a stage in order, as far
+    // ahead as the ring allows.
     const int rows_per_roi = C / kCS * Cfg<T>::kGBoxRows;
-    unsigned q = 0;
-    int it = blockIdx.x;
+    unsigned s = 0, phase = 0, q = 0;
+    int n_claimed = 0;
+    auto claim = [&]() -> int {
+      const int it = (int)blockIdx.x + n_claimed * (int)gridDim.x;
+      ++n_claimed;
+      return it < n_items ? it : -1;
+    };
+    int it = claim();
     int2 lc = make_int2(0, 0);
     int kk = 0;
-    if (it < n_items) {
+    if (it >= 0) {
       lc = __ldg(tile_list + it / tg.n_slices);
       kk = lane < lc.y ? __ldg(pair_k + lc.x + lane) : 0;
     }
-    while (it < n_items) {
+    while (it >= 0) {
       const int sl = it % tg.n_slices;
-      const int it_next = it + (int)gridDim.x;
+      const int it_next = claim();
       int2 lc_next = make_int2(0, 0);
       int kk_next = 0;
-      if (it_next < n_items) {
+      if (it_next >= 0) {
         lc_next = __ldg(tile_list + it_next / tg.n_slices);
         kk_next = lane < lc_next.y ? __ldg(pair_k + lc_next.x + lane) : 0;
       }
@@ -317,142 +443,209 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
         for (int i = 0; i < n; ++i, ++q) {
           const int k = __shfl_sync(0xffffffffu, kk, i);
           if (lane == 0) {
-            const unsigned s = q % NS;
             unsigned char* st = smem + (size_t)s * SB;
-            if (q >= (unsigned)NS) mbar_wait(&empty[s], ((q / NS) - 1u) & 1u);
+            if (q >= (unsigned)NS) OWN_WAIT(&empty[s], phase ^ 1u);
             mbar_expect_tx(&full[s], (unsigned)SB);
             tmap_load_2d(st, &tm_plan, 0, k * Cfg<T>::kPlanBoxRows, &full[s]);
             tmap_load_2d(st + sizeof(Plan), &tm_g, 0, k * rows_per_roi + sl * Cfg<T>::kGBoxRows, &full[s]);
           }
+          if (++s == (unsigned)NS) { s = 0; phase ^= 1u; }
         }
         __syncwarp();
       }
       it = it_next; lc = lc_next; kk = kk_next;
     }
-#else
-    // ------------------------------------------------------------------ producer: lane s owns ring stage s
-    if (lane < NS) {
-      unsigned char* st = smem + (size_t)lane * SB;
-      unsigned q_base = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const int t = it / tg.n_slices, sl = it - t * tg.n_slices;
-        const int2 lc = __ldg(tile_list + t);
-        const T* __restrict__ gsl = grad_out + (size_t)sl * kCS * kNB;
-        int p = (int)((unsigned)(lane + NS - (int)(q_base % NS)) % NS);
-        for (; p < lc.y; p += NS) {
-          const unsigned q = q_base + (unsigned)p;
-          if (q >= (unsigned)NS) mbar_wait(&empty[lane], ((q / NS) - 1u) & 1u);
-          const int k = __ldg(pair_k + lc.x + p);
-          mbar_expect_tx(&full[lane], (unsigned)SB);
-          bulk_load(st, plans + k, (unsigned)sizeof(Plan), &full[lane]);
-          bulk_load(st + sizeof(Plan), gsl + (size_t)k * C * kNB, (unsigned)Cfg<T>::kGBytes, &full[lane]);
-        }
-        q_base += (unsigned)lc.y;
-      }
-    }
-#endif
     return;
   }
 
-  // -------------------------------------------------------------------- consumers: tile rows 2*warp, 2*warp+1
-  const int r0 = 2 * warp;
+  if (warp == kWarps + 1) {
+    // ------------------------------------------------------------------ decoder: once per pair, intersects the RoI's live
+    // rows / columns with the tile and publishes the result in info[stage]
+    unsigned s = 0, phase = 0;
+    int2 lc_next = (int)blockIdx.x < n_items ? __ldg(tile_list + blockIdx.x / tg.n_slices) : make_int2(0, 0);
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const TileAt a = tile_at(tg, it / tg.n_slices);
+      const int2 lc = lc_next;
+      if (it + (int)gridDim.x < n_items) lc_next = __ldg(tile_list + (it + gridDim.x) / tg.n_slices);   // next item's list, early
+      for (int p = 0; p < lc.y; ++p) {
+        OWN_WAIT(&full[s], phase);
+        const Plan& P = *reinterpret_cast<const Plan*>(smem + (size_t)s * SB);
+        const int rel_r = lane < kMaxLive ? (int)P.rows[lane] - a.y0 : 0x7fff;      // padding entries are 0x7fff
+        const unsigned rowmask = __reduce_or_sync(0xffffffffu, (rel_r >= 0 && rel_r < kTileH) ? (1u << rel_r) : 0u);
+        const unsigned i_first = __popc(__ballot_sync(0xffffffffu, rel_r < 0));
+        const int4 hdr = *reinterpret_cast<const int4*>(&P);
+        const int x_first = (short)(hdr.z & 0xffff);
+        unsigned blocks = 0x80000000u, colmask = 0, j_first = 0;
+        int w_off = 0;
+        if (hdr.w & 0xffff) {
+          const int b_first = (a.x0 >> 2) - (x_first >> 2);                       // plan block of the tile's block 0 (-3 .. 7)
+          const unsigned long long all = *reinterpret_cast<const unsigned long long*>(P.blk);
+          blocks = (b_first >= 0 ? (unsigned)(all >> (8 * b_first)) : (unsigned)(all << (8 * -b_first))) & 0x07070707u;
+          w_off = b_first * kBlk;
+          colmask = blocks;                                                         // only "any live column" matters below
+        } else {
+          // the plan has no blocked form (columns far apart, or a block of the span needs more than 4 bins): try again
+          // for the 4 blocks of THIS tile from the A_x rows of its live columns; the general form is the last resort
+          const int rel_c = lane < kMaxLive ? (int)P.cols[lane] - a.x0 : 0x7fff;
+          colmask = __reduce_or_sync(0xffffffffu, (rel_c >= 0 && rel_c < kTileW) ? (1u << rel_c) : 0u);
+          j_first = __popc(__ballot_sync(0xffffffffu, rel_c < 0));
+          float row[8];
+          {
+            const bool live = lane < kTileW && ((colmask >> lane) & 1u);
+            const int j = (int)j_first + __popc(colmask & ((1u << lane) - 1u));
+            const float4 a0 = live ? *reinterpret_cast<const float4*>(&P.ax[j][0]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 a1 = live ? *reinterpret_cast<const float4*>(&P.ax[j][4]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            row[0] = a0.x; row[1] = a0.y; row[2] = a0.z; row[3] = a0.w; row[4] = a1.x; row[5] = a1.y; row[6] = a1.z; row[7] = 0.f;
+          }
+          unsigned nz = 0;
+#pragma unroll
+          for (int pw = 0; pw < kP; ++pw) nz |= row[pw] != 0.f ? 1u << pw : 0u;
+          int lo = nz ? __ffs(nz) - 1 : kP, hi = nz ? 31 - __clz(nz) : -1;
+          lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, 1)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 1));
+          lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, 2)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 2));
+          const int pb0 = min(lo, kP - kTaps);
+          const unsigned wide = __ballot_sync(0xffffffffu, lane < kTileW && hi > pb0 + kTaps - 1);
+          if (!wide) {
+            float4 wv;
+            wv.x = pb0 == 0 ? row[0] : pb0 == 1 ? row[1] : pb0 == 2 ? row[2] : row[3];
+            wv.y = pb0 == 0 ? row[1] : pb0 == 1 ? row[2] : pb0 == 2 ? row[3] : row[4];
+            wv.z = pb0 == 0 ? row[2] : pb0 == 1 ? row[3] : pb0 == 2 ? row[4] : row[5];
+            wv.w = pb0 == 0 ? row[3] : pb0 == 1 ? row[4] : pb0 == 2 ? row[5] : row[6];
+            if (lane < kTileW) info[s].wtab[lane] = wv;
+            blocks = 0;
+#pragma unroll
+            for (int b = 0; b < kTileW / kBlk; ++b) {
+              const int pb = __shfl_sync(0xffffffffu, pb0, b * kBlk), bh = __shfl_sync(0xffffffffu, hi, b * kBlk);
+              blocks |= ((unsigned)(pb & 3) | (bh >= 0 ? 4u : 0u)) << (8 * b);
+            }
+            w_off = kOwnTable;
+            __syncwarp();
+          }
+        }
+        if (lane == 0) {
+          PairInfo& I = info[s];
+          I.rowmask = colmask ? rowmask : 0u;          // no live column in this tile: nothing to do for any warp
+          I.i_first = i_first; I.blocks = blocks; I.w_off = w_off;
+          I.colmask = colmask; I.j_first = j_first;
+          mbar_arrive(&ready[s]);                      // release: the stores above are visible to whoever observes the phase
+        }
+        __syncwarp();
+        if (++s == (unsigned)NS) { s = 0; phase ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumers: tile rows kRPW*warp ..
+  const int r0 = kRPW * warp;
   unsigned q = 0;
 #ifdef DGOD_OWN_TIMING
   const long long t_start = clock64();
   long long t_wait = 0, t_store = 0;
 #endif
+  unsigned s = 0, phase = 0;                                // ring position of pair q
+  int2 lc_next = (int)blockIdx.x < n_items ? __ldg(tile_list + blockIdx.x / tg.n_slices) : make_int2(0, 0);
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-    const int t = it / tg.n_slices, sl = it - t * tg.n_slices;
-    const TileAt a = tile_at(tg, t);
-    const int2 lc = __ldg(tile_list + t);
-    const int y_mine = a.y0 + r0;
-    float2 acc0[kTileW], acc1[kTileW];
+    const int t_id = it / tg.n_slices, sl = it - t_id * tg.n_slices;
+    const TileAt a = tile_at(tg, t_id);
+    const int2 lc = lc_next;
+    if (it + (int)gridDim.x < n_items) lc_next = __ldg(tile_list + (it + gridDim.x) / tg.n_slices);   // next item's list, early
+    float2 acc[kRPW][kTileW];
 #pragma unroll
-    for (int x = 0; x < kTileW; ++x) acc0[x] = acc1[x] = make_float2(0.f, 0.f);
+    for (int r = 0; r < kRPW; ++r)
+#pragma unroll
+      for (int x = 0; x < kTileW; ++x) acc[r][x] = make_float2(0.f, 0.f);
 
     for (int p = 0; p < lc.y; ++p, ++q) {
-      const unsigned s = q % NS;
 #ifdef DGOD_OWN_TIMING
       const long long tw = clock64();
 #endif
-      mbar_wait(&full[s], (q / NS) & 1u);
+      OWN_WAIT(&ready[s], phase);
 #ifdef DGOD_OWN_TIMING
       t_wait += clock64() - tw;
 #endif
-      const unsigned char* st = smem + (size_t)s * SB;
-      const Plan& P = *reinterpret_cast<const Plan*>(st);
-      const int4 hdr = *reinterpret_cast<const int4*>(st);
-      const int n_cols = hdr.x >> 16;
-      const int y_first = (short)(hdr.y & 0xffff), y_last = hdr.y >> 16;
-      const int x_first = (short)(hdr.z & 0xffff), x_last = hdr.z >> 16;
-      const int span_mode = hdr.w & 0xffff;
-      // quick reject (warp-uniform): this warp's two rows or the tile's columns are outside the footprint box
-      if (y_mine + 1 >= y_first && y_mine <= y_last && x_last >= a.x0 && x_first < a.x0 + kTileW) {
-        // tile-relative coordinate of live row `lane`
-        const int rel_r = lane < kMaxLive ? (int)P.rows[lane] - a.y0 : 0x7fff;
-        const unsigned m0 = __ballot_sync(0xffffffffu, rel_r == r0), m1 = __ballot_sync(0xffffffffu, rel_r == r0 + 1);
-        if (m0 | m1) {
-          float ay0[8], ay1[8];
-          unsigned phm;                                    // bins whose samples put weight on either row (ballot: provably uniform)
-          {
-            const int i0 = m0 ? __ffs(m0) - 1 : 0, i1 = m1 ? __ffs(m1) - 1 : 0;
-            const float4* pa = reinterpret_cast<const float4*>(P.ay[i0]);
-            const float4* pb = reinterpret_cast<const float4*>(P.ay[i1]);
-            const float e0 = P.ay[i0][lane & 7], e1 = P.ay[i1][lane & 7];
-            phm = __ballot_sync(0xffffffffu, lane < kP && ((m0 && e0 != 0.f) || (m1 && e1 != 0.f)));
-            const float4 u0 = pa[0], u1 = pa[1], v0 = pb[0], v1 = pb[1];
-            const float z0 = m0 ? 1.f : 0.f, z1 = m1 ? 1.f : 0.f;
-            ay0[0] = u0.x * z0; ay0[1] = u0.y * z0; ay0[2] = u0.z * z0; ay0[3] = u0.w * z0;
-            ay0[4] = u1.x * z0; ay0[5] = u1.y * z0; ay0[6] = u1.z * z0;
-            ay1[0] = v0.x * z1; ay1[1] = v0.y * z1; ay1[2] = v0.z * z1; ay1[3] = v0.w * z1;
-            ay1[4] = v1.x * z1; ay1[5] = v1.y * z1; ay1[6] = v1.z * z1;
-          }
-          float2 t0[kP], t1[kP];
+      const uint4 ia = *reinterpret_cast<const uint4*>(&info[s]);               // rowmask, i_first, blocks, w_off
+      const unsigned rm = (ia.x >> r0) & ((1u << kRPW) - 1u);
+      {
+        if (rm) {
+        const unsigned char* st = smem + (size_t)s * SB;
+        const Plan& P = *reinterpret_cast<const Plan*>(st);
+        int idx[kRPW];
+        {
+          const int i0 = (int)ia.y + __popc(ia.x & ((1u << r0) - 1u));          // list index of this warp's first live row
 #pragma unroll
-          for (int pw = 0; pw < kP; ++pw) t0[pw] = t1[pw] = make_float2(0.f, 0.f);
-          const T* __restrict__ ga = reinterpret_cast<const T*>(st + sizeof(Plan)) + lane * kNB;
-          const T* __restrict__ gb = ga + 32 * kNB;
+          for (int r = 0; r < kRPW; ++r) idx[r] = ((rm >> r) & 1u) ? i0 + __popc(rm & ((1u << r) - 1u)) : i0;
+        }
+        float ay[kRPW][8];
+        unsigned phm = 0;
 #pragma unroll
-          for (int ph = 0; ph < kP; ++ph) {
-            if ((phm >> ph) & 1u) {                         // warp-uniform
+        for (int r = 0; r < kRPW; ++r) {
+          const bool live = (rm >> r) & 1u;
+          const float z = live ? 1.f : 0.f;                                     // a dead row reads row 0 of the table, times zero
+          const float4* pa = reinterpret_cast<const float4*>(P.ay[idx[r]]);
+          const float4 u0 = pa[0], u1 = pa[1];
+          ay[r][0] = u0.x * z; ay[r][1] = u0.y * z; ay[r][2] = u0.z * z; ay[r][3] = u0.w * z;
+          ay[r][4] = u1.x * z; ay[r][5] = u1.y * z; ay[r][6] = u1.z * z;
+          phm |= live ? (unsigned)P.aymask[idx[r]] : 0u;
+        }
+        float2 t[kRPW][kP];
 #pragma unroll
-              for (int pw = 0; pw < kP; ++pw) {
-                const float2 gv = make_float2(lds_as_f32<T>(ga + ph * kP + pw), lds_as_f32<T>(gb + ph * kP + pw));
-                t0[pw] = __ffma2_rn(make_float2(ay0[ph], ay0[ph]), gv, t0[pw]);
-                t1[pw] = __ffma2_rn(make_float2(ay1[ph], ay1[ph]), gv, t1[pw]);
-              }
+        for (int r = 0; r < kRPW; ++r)
+#pragma unroll
+          for (int pw = 0; pw < kP; ++pw) t[r][pw] = make_float2(0.f, 0.f);
+        const T* __restrict__ ga = reinterpret_cast<const T*>(st + sizeof(Plan)) + lane * kNB;
+        const T* __restrict__ gb = ga + 32 * kNB;
+#ifndef DGOD_OWN_SKIP_T
+#pragma unroll
+        for (int ph = 0; ph < kP; ++ph) {
+          if ((phm >> ph) & 1u) {                           // warp-uniform
+#pragma unroll
+            for (int pw = 0; pw < kP; ++pw) {
+              const float2 gv = make_float2(lds_as_f32<T>(ga + ph * kP + pw), lds_as_f32<T>(gb + ph * kP + pw));
+#pragma unroll
+              for (int r = 0; r < kRPW; ++r) t[r][pw] = __ffma2_rn(make_float2(ay[r][ph], ay[r][ph]), gv, t[r][pw]);
             }
           }
-          if (span_mode) {
-            // the live columns are consecutive: table row of tile column x is x + shift, a fixed offset per pair
-            const int shift = a.x0 - x_first;
-            const int xa = max(0, -shift), xb = min(kTileW - 1, n_cols - 1 - shift);
-            const unsigned cm = __ballot_sync(0xffffffffu, lane >= xa && lane <= xb);   // through a vote: provably uniform
-            const float4* base = reinterpret_cast<const float4*>(&P.ax[0][0]) + 2 * shift;
+        }
+#else
 #pragma unroll
-            for (int x = 0; x < kTileW; ++x) {
-              if ((cm >> x) & 1u) {                         // warp-uniform
-                const float4 w0 = base[2 * x], w1 = base[2 * x + 1];
-                column_update(w0, w1, t0, t1, acc0[x], acc1[x]);
-              }
-            }
-          } else {
-            const int rel_c = lane < kMaxLive ? (int)P.cols[lane] - a.x0 : 0x7fff;
-            const unsigned cm = __reduce_or_sync(0xffffffffu, (rel_c >= 0 && rel_c < kTileW) ? (1u << rel_c) : 0u);
-            const int j_first = __popc(__ballot_sync(0xffffffffu, rel_c < 0));
+        for (int r = 0; r < kRPW; ++r)
 #pragma unroll
-            for (int x = 0; x < kTileW; ++x) {
-              if ((cm >> x) & 1u) {                         // warp-uniform
-                const int j = j_first + __popc(cm & ((1u << x) - 1u));
-                const float4* px = reinterpret_cast<const float4*>(P.ax[j]);
-                column_update(px[0], px[1], t0, t1, acc0[x], acc1[x]);
-              }
+          for (int pw = 0; pw < kP; ++pw) t[r][pw] = make_float2(ay[r][pw] + (float)phm, lds_as_f32<T>(ga + pw));
+#endif
+#ifdef DGOD_OWN_SKIP_COLS
+#pragma unroll
+        for (int r = 0; r < kRPW; ++r)
+#pragma unroll
+          for (int pw = 0; pw < kP; ++pw) acc[r][pw] = __fadd2_rn(acc[r][pw], t[r][pw]);
+#else
+        if (!(ia.z >> 31)) {
+          // blocked form: the 4 absolute column blocks of this tile, branch-free inside a block
+          const float4* w = (int)ia.w == kOwnTable ? info[s].wtab : &P.wblk[0][0] + (int)ia.w;   // absent blocks are never read
+          column_block_any<0>(ia.z, w, t, acc);
+          column_block_any<1>(ia.z, w, t, acc);
+          column_block_any<2>(ia.z, w, t, acc);
+          column_block_any<3>(ia.z, w, t, acc);
+        } else {
+          // general form (columns far apart, or more than 4 bins on a block): all 7 bins per live column
+          const uint4 ib = *(reinterpret_cast<const uint4*>(&info[s]) + 1);      // colmask, j_first
+          const unsigned cm = ib.x;
+          const int j_first = (int)ib.y;
+#pragma unroll
+          for (int x = 0; x < kTileW; ++x) {
+            if ((cm >> x) & 1u) {                           // warp-uniform
+              const int j = j_first + __popc(cm & ((1u << x) - 1u));
+              const float4* px = reinterpret_cast<const float4*>(P.ax[j]);
+              column_dense(px[0], px[1], t, acc, x);
             }
           }
+        }
+#endif
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
+      if (++s == (unsigned)NS) { s = 0; phase ^= 1u; }
     }
 
     // ---- the tile leaves once, zeros included
@@ -462,17 +655,27 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
     const int H = g.H[a.level], W = g.W[a.level];
     T* __restrict__ img = reinterpret_cast<T*>(g.gfeat[a.level]) + (size_t)a.b * H * W * C + (size_t)sl * kCS + lane;
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const int y = a.y0 + r0 + rr;
+    for (int r = 0; r < kRPW; ++r) {
+      const int y = a.y0 + r0 + r;
+#ifdef DGOD_OWN_SKIP_STORE
+      if (y < H && acc[r][3].x == 123.456f) {
+#else
       if (y < H) {
-        T* __restrict__ rowp = img + (size_t)y * W * C;
+#endif
+        T* __restrict__ rowp = img + ((size_t)y * W + a.x0) * C;
+        if (a.x0 + kTileW <= W) {
 #pragma unroll
-        for (int x = 0; x < kTileW; ++x) {
-          const int X = a.x0 + x;
-          if (X < W) {
-            const float2 v = rr ? acc1[x] : acc0[x];
-            rowp[(size_t)X * C] = from_f32<T>(v.x);
-            rowp[(size_t)X * C + 32] = from_f32<T>(v.y);
+          for (int x = 0; x < kTileW; ++x) {
+            rowp[(size_t)x * C] = from_f32<T>(acc[r][x].x);
+            rowp[(size_t)x * C + 32] = from_f32<T>(acc[r][x].y);
+          }
+        } else {
+#pragma unroll
+          for (int x = 0; x < kTileW; ++x) {
+            if (a.x0 + x < W) {
+              rowp[(size_t)x * C] = from_f32<T>(acc[r][x].x);
+              rowp[(size_t)x * C + 32] = from_f32<T>(acc[r][x].y);
+            }
           }
         }
       }
@@ -482,8 +685,8 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
 #endif
   }
 #ifdef DGOD_OWN_TIMING
-  if (lane == 0 && (warp == 0 || warp == kWarps - 1)) {      // two warps per CTA: total, waiting for a stage, storing, pairs
-    long long* o = timing + ((size_t)blockIdx.x * 2 + (warp ? 1 : 0)) * 4;
+  if (lane == 0) {      // per CTA and consumer warp: total, waiting for a stage, storing, pairs
+    long long* o = timing + ((size_t)blockIdx.x * kWarps + warp) * 4;
     o[0] = clock64() - t_start; o[1] = t_wait; o[2] = t_store; o[3] = q;
   }
 #endif
@@ -575,11 +778,10 @@ static int launch_own(const RoiDev& g, const own::Tiles& tg, const OwnLayout& L,
                                                                                       pair_k, cursor);
   DGOD_LAUNCHED();
   const int n_items = tg.n_tiles * tg.n_slices;
-  const int grid = n_items < n_sm ? n_items : n_sm;
+  const int grid = std::min(n_items, n_sm);
   CUtensorMap tm_plan, tm_g;
   memset(&tm_plan, 0, sizeof(tm_plan));
   memset(&tm_g, 0, sizeof(tm_g));
-#if DGOD_OWN_TMAP
   {
     using CF = own::Cfg<T>;
     const unsigned long long K = n_rois > 0 ? n_rois : 1;
@@ -590,9 +792,8 @@ static int launch_own(const RoiDev& g, const own::Tiles& tg, const OwnLayout& L,
                          CF::kGBoxRows);
     if (rc) return rc;
   }
-#endif
-  own::own_bwd_kernel<T><<<grid, own::kThreads, own::Cfg<T>::kSmem, st>>>(g, tg, tm_plan, tm_g, plans, (const T*)grad_out, tile_list,
-                                                                       pair_k, reinterpret_cast<long long*>(ws + 1024));
+  own::own_bwd_kernel<T><<<grid, own::kThreads, own::Cfg<T>::kSmem, st>>>(g, tg, tm_plan, tm_g, tile_list, pair_k,
+                                                                       reinterpret_cast<long long*>(ws + 1024));
   DGOD_LAUNCHED();
   return DGOD_OK;
 }

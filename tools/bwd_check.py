@@ -26,6 +26,7 @@ ap.add_argument("--hw", default="608x1024")
 ap.add_argument("--iters", type=int, default=15)
 ap.add_argument("--offsets", type=int, default=1)
 ap.add_argument("--lib", default="", help="a variant library built by tools/roi_variants.py (tools/_variants/lib_<tag>.so)")
+ap.add_argument("--warps", type=int, default=28, help="consumer warps per CTA of the timing build")
 ap.add_argument("--timing", action="store_true", help="read the per-CTA cycle counters of a -DDGOD_OWN_TIMING build")
 a = ap.parse_args()
 
@@ -80,9 +81,11 @@ for algo in (int(v) for v in a.algos.split(",")):
         msg += "  relerr vs first: " + " ".join(f"{e:.2e}" for e in errs)
     print(msg, flush=True)
     if a.timing and algo == 4:
-        t = ws[1024:1024 + 148 * 2 * 4 * 8].view(torch.int64).view(148, 2, 4).cpu().double()
-        for w in (0, 1):
-            tot, wait, store, pairs = (t[:, w, i] for i in range(4))
-            print(f"  warp {'0' if w == 0 else 'last'}: total cycles min/mean/max {tot.min():.0f}/{tot.mean():.0f}/{tot.max():.0f}  "
-                  f"waiting for stages mean {wait.mean():.0f} max {wait.max():.0f}  storing mean {store.mean():.0f}  "
-                  f"pairs min/mean/max {pairs.min():.0f}/{pairs.mean():.0f}/{pairs.max():.0f}")
+        t = ws[1024:1024 + 148 * a.warps * 4 * 8].view(torch.int64).view(148, a.warps, 4).cpu().double()
+        tot, wait, store, pairs = (t[..., i] for i in range(4))
+        busy = tot - wait - store
+        print(f"  per CTA (slowest warp) total cycles min/mean/max {tot.max(1).values.min():.0f}/{tot.max(1).values.mean():.0f}/{tot.max(1).values.max():.0f}  "
+              f"pairs per CTA min/mean/max {pairs[:, 0].min():.0f}/{pairs[:, 0].mean():.0f}/{pairs[:, 0].max():.0f}")
+        print("  per warp position (mean over CTAs): busy " + " ".join(f"{v / 1e3:.0f}k" for v in busy.mean(0)))
+        print("                                      wait " + " ".join(f"{v / 1e3:.0f}k" for v in wait.mean(0)))
+        print(f"  store mean {store.mean():.0f}; busiest warp of a CTA / mean warp of that CTA = {(busy.max(1).values / busy.mean(1)).mean():.2f}")
