@@ -251,7 +251,10 @@ class DGFCOS(nn.Module):
     def training_step(self, batch) -> Tensor:
         imgs = list(batch[0])
         targets = [{"boxes": b.float(), "labels": l.long()} for b, l in zip(batch[1], batch[2])]
-        domain = batch[3]
+        # batch[3] is a host tensor in the reference (DGcommon.collate_fn; `.to(device=0)` at DGFCOS.py:186): the per-image
+        # loops of modes 2-4 read the ids from it for free; a device tensor costs one device->host read there
+        dom_src = batch[3]
+        domain = dom_src.to(imgs[0].device, non_blocking=True)
         if self.mode == 0:
             loss_dict = self.detector(imgs, targets)
             loss = loss_dict["classification"] + loss_dict["bbox_regression"] + loss_dict["bbox_ctrness"]
@@ -268,7 +271,7 @@ class DGFCOS(nn.Module):
             loss = loss + self.reg_weights[2] * F.mse_loss(img_scores.unsqueeze(1).repeat(1, n_loc, 1), ida)
             self.mode = 0
             return loss
-        dom = domain.tolist()
+        dom = dom_src.tolist()
         losses = []
         if self.mode == 2:                                 # DGFCOS.py:196-208: detector frozen, InsCls learn
             for head in self.InsCls:
