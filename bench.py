@@ -503,6 +503,7 @@ def cpu_reference_sample(model_name: str, exp: str, steps: int, warmup: int, bat
     modes = cycle_modes(exp)
     if ref_real.available():
         kind = "reference"
+        ref_real.load(cpu_shims=True)       # on a GPU box too: this arm is the reference on the HOST cores
         build = ref_real.build_dgfrcnn if model_name == "frcnn" else ref_real.build_dgfcos
         model = build(9, batch, exp, REG_WEIGHTS, n_dom).train()
         calibrate(model.detector, batches[0][0] + batches[1][0])

@@ -1,19 +1,20 @@
 """Data-parallel gradient synchronisation for the DG training loops: one process per GPU,
 identical replicas, NCCL all-reduce (mean) of the gradients over NVLink / NVSwitch — overlapped with backward.
 
-* Every parameter's `.grad` is a VIEW of one persistent flat buffer, laid out in reverse registration order
-  (roughly the order in which backward produces gradients) and cut into buckets.  There is no concatenation
-  before the all-reduce and no copy back after it.
-* A post-accumulate-grad hook per parameter counts arrivals; when the last gradient a bucket expects for the
-  current schedule key (the DG mode) has arrived, the bucket's all-reduce is enqueued asynchronously on NCCL's
-  stream while backward continues.  Which parameters receive a gradient depends on the mode (DGFRCNN.py:
-  125-199 touches different heads in different modes): the expectation is learned the first time a key is seen
-  (everything then goes out in `finish()`), and checked on later steps.
-* The layout never depends on the data: a parameter without a gradient on this rank contributes zeros, so ranks
-  whose local batches touch different heads (the per-image loops of modes 2-4) still reduce matching buffers.
-* The reference's optimizer skips parameters whose `.grad` is None (they get no weight decay).  `finish()`
-  reproduces that: a parameter no rank touched in this step has its `.grad` detached to None for the optimizer
-  step and re-attached to its view afterwards (`restore()`).
+* One persistent flat buffer holds every trainable parameter's gradient, laid out in reverse registration order
+  (roughly the order in which backward produces gradients) and cut into buckets; each parameter has a VIEW into it
+  with the parameter's own strides (channels_last weights get channels_last views).
+* Backward runs with `.grad = None`, so autograd hands every parameter its gradient tensor without an extra
+  accumulate kernel.  A post-accumulate-grad hook per parameter counts arrivals; when the last gradient a bucket
+  expects for the current schedule key (the DG mode) has arrived, the bucket is packed with ONE multi-tensor copy and
+  its all-reduce is enqueued asynchronously on NCCL's stream while backward continues.  Which parameters receive a
+  gradient depends on the mode (DGFRCNN.py:125-199 touches different heads in different modes): the expectation is
+  learned the first time a key is seen (everything then goes out in `finish()`).
+* The layout never depends on the data: a parameter without a gradient on this rank contributes zeros, so ranks whose
+  local batches touch different heads (the per-image loops of modes 2-4) still reduce matching buffers.
+* After `finish()` a touched parameter's `.grad` IS its view of the reduced buffer (no copy back); a parameter no
+  rank touched keeps `.grad = None`, so the optimizer skips it exactly as it does for the reference (no weight decay
+  on heads the step did not use).
 
 Works on gloo (CPU tests, world size 2) and NCCL.
 """
@@ -24,6 +25,19 @@ from typing import Dict, Hashable, List, Optional, Sequence
 import torch
 import torch.distributed as dist
 from torch import Tensor
+
+
+def _view_like(flat: Tensor, p: Tensor) -> Tensor:
+    """A view of the 1-D `flat` (p.numel() elements) with p's shape AND p's strides when p is dense in some permutation
+    of its dimensions (contiguous, channels_last, ...); contiguous otherwise."""
+    if p.is_contiguous() or p.dim() < 2:
+        return flat.view(p.shape)
+    order = sorted(range(p.dim()), key=lambda d: (-p.stride(d), d))           # dimensions from outermost to innermost
+    shape = [p.shape[d] for d in order]
+    v = flat.view(shape)
+    inv = [order.index(d) for d in range(p.dim())]
+    v = v.permute(inv)
+    return v if v.stride() == p.stride() else flat.view(p.shape)
 
 
 class GradSync:
@@ -39,82 +53,91 @@ class GradSync:
             raise ValueError("GradSync: parameters must share dtype and device")
         order = list(reversed(range(len(self.params))))           # backward produces the last layers' gradients first
         esz = p0.element_size()
-        self.offsets: Dict[int, int] = {}
+        offsets: Dict[int, int] = {}
         self.bucket_of: Dict[int, int] = {}
         self.bucket_ranges: List[List[int]] = []                   # [start, end) element ranges of the flat buffer
-        off, start, b = 0, 0, 0
+        self.members: List[List[int]] = [[]]
+        off, start = 0, 0
         for i in order:
             n = self.params[i].numel()
-            n_pad = (n + 31) // 32 * 32                            # keep every view 128-byte aligned
-            self.offsets[i] = off
-            self.bucket_of[i] = b
-            off += n_pad
+            offsets[i] = off
+            self.bucket_of[i] = len(self.bucket_ranges)
+            self.members[-1].append(i)
+            off += (n + 31) // 32 * 32                             # keep every view 128-byte aligned
             if (off - start) * esz >= bucket_bytes:
                 self.bucket_ranges.append([start, off])
-                start, b = off, b + 1
+                self.members.append([])
+                start = off
         if off > start:
             self.bucket_ranges.append([start, off])
+        else:
+            self.members.pop()
         self.flat = torch.zeros(off + len(self.params), dtype=p0.dtype, device=p0.device)
         self.flags = self.flat[off:]                               # one element per parameter: touched on some rank
         self.n_flat = off
-        self.views = [self.flat[self.offsets[i]:self.offsets[i] + p.numel()].view_as(p) for i, p in enumerate(self.params)]
-        for p, v in zip(self.params, self.views):
-            p.grad = v
+        self.views = [_view_like(self.flat[offsets[i]:offsets[i] + p.numel()], p) for i, p in enumerate(self.params)]
         self._touched = [False] * len(self.params)
         self._arrived = [0] * len(self.bucket_ranges)
         self._launched: List[Optional[object]] = [None] * len(self.bucket_ranges)
+        self._packed = [False] * len(self.bucket_ranges)
         self._expected: Dict[Hashable, List[int]] = {}
-        self._touched_sets: Dict[Hashable, frozenset] = {}
         self._key: Hashable = None
-        self._detached: List[int] = []
         self.use_avg = self.world > 1 and dist.is_initialized() and dist.get_backend(process_group) == "nccl"
         for i, p in enumerate(self.params):
             p.register_post_accumulate_grad_hook(self._make_hook(i))
 
     # ------------------------------------------------------------------ per-step protocol
     def begin(self, key: Hashable = None) -> None:
-        """Call before backward: zeroes the flat buffer (one kernel instead of one per parameter) and arms the
-        bucket counters for schedule key `key`."""
-        self.restore()
+        """Call before backward: clears the flat buffer (one kernel) and every `.grad`, arms the bucket counters for
+        schedule key `key`."""
         self.flat.zero_()
+        for p in self.params:
+            p.grad = None
         self._key = key
         self._touched = [False] * len(self.params)
         self._arrived = [0] * len(self.bucket_ranges)
         self._launched = [None] * len(self.bucket_ranges)
+        self._packed = [False] * len(self.bucket_ranges)
 
     def _make_hook(self, i: int):
+        b = self.bucket_of[i]
+
         def hook(p: Tensor):
-            if p.grad is not self.views[i]:                         # autograd replaced the view (first use): fold it back
-                self.views[i].copy_(p.grad)
-                p.grad = self.views[i]
             if self._touched[i]:
                 return
             self._touched[i] = True
-            b = self.bucket_of[i]
             self._arrived[b] += 1
             exp = self._expected.get(self._key)
             if self.world > 1 and exp is not None and exp[b] > 0 and self._arrived[b] == exp[b]:
-                self._reduce_bucket(b)
+                self._send_bucket(b)
         return hook
 
-    def _reduce_bucket(self, b: int) -> None:
-        s, e = self.bucket_ranges[b]
-        op = dist.ReduceOp.AVG if self.use_avg else dist.ReduceOp.SUM
-        self._launched[b] = dist.all_reduce(self.flat[s:e], op=op, group=self.group, async_op=True)
+    def _send_bucket(self, b: int) -> None:
+        """Packs the gradients that arrived for bucket b into its slice of the flat buffer (one multi-tensor copy) and
+        starts its all-reduce."""
+        src = [self.params[i].grad for i in self.members[b] if self._touched[i] and self.params[i].grad is not None]
+        dst = [self.views[i] for i in self.members[b] if self._touched[i] and self.params[i].grad is not None]
+        if src:
+            torch._foreach_copy_(dst, src)
+        self._packed[b] = True
+        if self.world > 1:
+            s, e = self.bucket_ranges[b]
+            op = dist.ReduceOp.AVG if self.use_avg else dist.ReduceOp.SUM
+            self._launched[b] = dist.all_reduce(self.flat[s:e], op=op, group=self.group, async_op=True)
 
     def finish(self, consistent_across_ranks: bool = True) -> None:
-        """Call after backward, before optimizer.step(): sends the buckets that were not sent from the hooks, waits
-        for all of them, and hides from the optimizer the parameters that no rank touched.  With
-        `consistent_across_ranks=False` (per-image loops whose heads depend on the local domain ids) the touched
-        flags are reduced too, at the price of one small device->host read."""
-        touched = self._touched
+        """Call after backward, before optimizer.step(): sends the buckets that were not sent from the hooks, waits for
+        all of them and points every touched parameter's `.grad` at its view of the reduced buffer.  With
+        `consistent_across_ranks=False` (per-image loops whose heads depend on the local domain ids) the touched flags
+        are reduced too, at the price of one small device->host read."""
+        touched = list(self._touched)
+        work_flags = None
+        if self.world > 1 and not consistent_across_ranks:
+            self.flags.copy_(torch.tensor([1.0 if t else 0.0 for t in touched], dtype=self.flat.dtype))
+        for b in range(len(self.bucket_ranges)):
+            if not self._packed[b]:
+                self._send_bucket(b)
         if self.world > 1:
-            late = [b for b in range(len(self.bucket_ranges)) if self._launched[b] is None]
-            if not consistent_across_ranks:
-                self.flags.copy_(torch.tensor([1.0 if t else 0.0 for t in touched], dtype=self.flat.dtype), non_blocking=False)
-            for b in late:
-                self._reduce_bucket(b)
-            work_flags = None
             if not consistent_across_ranks:
                 work_flags = dist.all_reduce(self.flags, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             for w in self._launched:
@@ -125,25 +148,19 @@ class GradSync:
             if work_flags is not None:
                 work_flags.wait()
                 touched = [v > 0 for v in self.flags.tolist()]
-            key = self._key
             counts = [0] * len(self.bucket_ranges)
             for i, t in enumerate(self._touched):
                 if t:
                     counts[self.bucket_of[i]] += 1
-            known = self._expected.get(key)
-            if known is None or known != counts:
-                # first time this key is seen (or the touched set changed): remember it; buckets whose expectation
-                # was wrong went out late, which costs overlap but never correctness
-                self._expected[key] = counts
-        self._detached = [i for i, t in enumerate(touched) if not t]
-        for i in self._detached:
-            self.params[i].grad = None
+            if self._expected.get(self._key) != counts:
+                # first time this key is seen (or the touched set changed): remember it; buckets whose expectation was
+                # wrong went out late, which costs overlap but never correctness
+                self._expected[self._key] = counts
+        for i, t in enumerate(touched):
+            self.params[i].grad = self.views[i] if t else None
 
     def restore(self) -> None:
-        """Re-attach the gradient views that `finish()` hid from the optimizer."""
-        for i in self._detached:
-            self.params[i].grad = self.views[i]
-        self._detached = []
+        """Kept for API compatibility: nothing to undo (untouched parameters simply have `.grad = None`)."""
 
 
 def allreduce_gradients(params, world_size: int) -> None:

@@ -158,7 +158,7 @@ class RegionProposalNetwork(nn.Module):
         grids = [tuple(o.shape[-2:]) for o in objectness]
         ph, pw = image_tensor_shape[-2:]
         strides = [(ph // g[0], pw // g[1]) for g in grids]                # TV anchor_utils.py:119-125
-        sizes = torch.tensor([[float(h), float(w)] for h, w in image_sizes], dtype=torch.float32, device=dev)
+        sizes = ops.device_constant(tuple((float(h), float(w)) for h, w in image_sizes), torch.float32, dev)
         boxes, scores, counts = ops.rpn_proposals(                          # fasterrcnn.py:166-182
             objectness, deltas, sizes, strides, [c.tolist() for c in self.cells],
             self.pre_nms_top_n(), self.post_nms_top_n(), self.nms_thresh, self.min_size, self.score_thresh)
@@ -280,14 +280,14 @@ class RoIHeads(nn.Module):
         seg = [n * nc for n in boxes_per_image]
         keep, info = ops.nms_segments(cb.view(-1, 4), cs.view(-1), cl.view(-1), seg, self.nms_thresh,
                                       valid=cv.view(-1), max_out_per_seg=self.detections_per_img)
-        off = ops._offsets(seg, cb.device)[:-1].to(torch.int64)
+        off = ops.device_constant(tuple(sum(seg[:i]) for i in range(len(seg))), torch.int64, cb.device)
         flat = keep + off[:, None]
         return (cb.view(-1, 4)[flat], cs.view(-1)[flat], cl.view(-1)[flat], info[:-1])
 
     def forward(self, features, proposals: List[Tensor], image_sizes: List[Tuple[int, int]], targets=None,
                 sampler_keys=None):
         dev = proposals[0].device
-        sizes_t = torch.tensor([[float(h), float(w)] for h, w in image_sizes], dtype=torch.float32, device=dev)
+        sizes_t = ops.device_constant(tuple((float(h), float(w)) for h, w in image_sizes), torch.float32, dev)
         labels = reg_targets = None
         if self.training:
             props, _, labels, reg_targets = self.select_training_samples(proposals, targets, sampler_keys)

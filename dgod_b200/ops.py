@@ -43,19 +43,59 @@ def _need_cuda(*ts: Optional[Tensor]):
             raise RuntimeError("dgod_b200 ops need CUDA tensors (sm_100a); there is no CPU fallback")
 
 
+# Per-call host overhead matters as much as the kernels for the latency-bound ops (a 20 us kernel behind 100 us of
+# wrapper), so the small things a call needs are cached instead of rebuilt:
+#   * scratch workspaces: one growing buffer per (device, stream) — kernels of one stream run in order, so the next
+#     call may reuse the bytes of the previous one; nothing in a workspace outlives the call that filled it;
+#   * offset vectors (`gt_offsets`, `seg_offsets`, `roi_img_offsets`) and other tiny host-built tensors: keyed by
+#     their values — the counts repeat from step to step (512 RoIs per image, 20 boxes per image, ...), and a
+#     `torch.tensor(list, device=cuda)` is a pageable host->device copy that stalls the launching thread.
+_WS_CACHE: dict = {}
+_CONST_CACHE: dict = {}
+_CONST_CACHE_MAX = 4096
+
+
 def _ws(nbytes: int, device) -> Tensor:
-    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+    n = max(int(nbytes), 1)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
+    buf = _WS_CACHE.get(key)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 1 << 20) * 5 // 4, dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = buf
+    return buf
 
 
 def _f32c(t: Tensor) -> Tensor:
     return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
 
 
+def device_constant(values, dtype, device) -> Tensor:
+    """A small read-only device tensor holding `values` (nested tuples / lists of numbers), cached by value."""
+    key = (repr(values), dtype, str(device))
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        if len(_CONST_CACHE) >= _CONST_CACHE_MAX:
+            _CONST_CACHE.clear()
+        t = torch.tensor(values, dtype=dtype, device=device)
+        _CONST_CACHE[key] = t
+    return t
+
+
 def _offsets(counts: Sequence[int], device) -> Tensor:
     off = [0]
     for c in counts:
         off.append(off[-1] + int(c))
-    return torch.tensor(off, dtype=torch.int32, device=device)
+    return device_constant(tuple(off), torch.int32, device)
+
+
+def _eager(op):
+    """The Python body of a `torch.library.custom_op`.  The ops stay registered (`torch.ops.dgod_b200.*`: CUDA kernel,
+    fake / meta kernel, autograd) for dispatcher users and torch.compile; the eager entry points of this module call the
+    body directly — the custom_op wrapper costs 60-100 us per call (schema checks, dispatcher round trip, autograd
+    bookkeeping), more than most of the kernels behind it."""
+    if torch.compiler.is_compiling():
+        return op
+    return getattr(op, "_init_fn", op)
 
 
 class KernelTimer:
@@ -114,7 +154,7 @@ def box_iou(boxes1: Tensor, boxes2: Tensor) -> Tensor:
     """TV ops/boxes.py:344-370 (xyxy only): [N,4] x [M,4] -> [N,M] IoU, fp32 bit-exact."""
     if boxes1.dim() != 2 or boxes2.dim() != 2 or boxes1.shape[-1] != 4 or boxes2.shape[-1] != 4:
         raise ValueError("box_iou expects boxes of shape [N, 4] and [M, 4]")
-    return _box_iou_op(boxes1, boxes2)
+    return _eager(_box_iou_op)(boxes1, boxes2)
 
 
 # --------------------------------------------------------------------------------- NMS
@@ -161,7 +201,7 @@ def nms_segments(boxes: Tensor, scores: Tensor, groups: Optional[Tensor], seg_co
     Returns (keep [n_seg, stride] segment-relative indices, info int32 [n_seg+1] = counts + status)."""
     seg_offsets = _offsets(seg_counts, boxes.device)
     max_len = max([int(c) for c in seg_counts], default=0)
-    return _nms_batched_op(boxes, scores, groups, valid, seg_offsets, max_len, float(iou_threshold),
+    return _eager(_nms_batched_op)(boxes, scores, groups, valid, seg_offsets, max_len, float(iou_threshold),
                            bool(offset_mode), int(max_out_per_seg))
 
 
@@ -313,7 +353,7 @@ def match_boxes(gt_boxes: Sequence[Tensor], boxes, high_threshold: float, low_th
     mask = 0
     for w in want:
         mask |= bits[w]
-    idx, lf, li, ci, mb = _iou_match_op(gt_cat, gl_cat, gt_off, bx, box_off, max_n, float(high_threshold),
+    idx, lf, li, ci, mb = _eager(_iou_match_op)(gt_cat, gl_cat, gt_off, bx, box_off, max_n, float(high_threshold),
                                         float(low_threshold), bool(allow_low_quality_matches), mask)
     out = {"matched_idx": idx}
     for name, t in (("labels_f32", lf), ("labels_i64", li), ("clamped_idx", ci), ("matched_boxes", mb)):
@@ -415,7 +455,7 @@ def fcos_assign(anchors: Tensor, gt_boxes: Sequence[Tensor], num_anchors_per_lev
     gt_off = _offsets([g.shape[0] for g in gt_boxes], dev)
     want = gt_labels is not None and num_classes > 0
     gl_cat = torch.cat([l.reshape(-1).to(torch.int64) for l in gt_labels]).contiguous() if want else None
-    idx, cls, bt, oh = _fcos_assign_op(anchors, int(num_anchors_per_level[0]), int(num_anchors_per_level[-1]),
+    idx, cls, bt, oh = _eager(_fcos_assign_op)(anchors, int(num_anchors_per_level[0]), int(num_anchors_per_level[-1]),
                                        float(center_sampling_radius), gt_cat, gl_cat, gt_off, int(num_classes), want)
     if want:
         return idx, cls, bt, oh
@@ -478,6 +518,24 @@ def _fcos_loss_backward(ctx, grad):
 _fcos_loss_op.register_autograd(_fcos_loss_backward, setup_context=_fcos_loss_setup)
 
 
+class _FcosLossFn(torch.autograd.Function):
+    """Eager path of dgod_b200::fcos_loss (same kernels, no dispatcher round trip)."""
+
+    @staticmethod
+    def forward(ctx, cls_logits, reg, ctr, anchors, ct, bt, alpha):
+        out = _fcos_loss_op._init_fn(cls_logits, reg, ctr, anchors, ct, bt, alpha)
+        ctx.save_for_backward(cls_logits, reg, ctr, anchors, ct, bt, out)
+        ctx.alpha = alpha
+        ctx.mark_non_differentiable()
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        cls_logits, reg, ctr, anchors, ct, bt, losses = ctx.saved_tensors
+        g = _fcos_loss_bwd_op._init_fn(cls_logits, reg, ctr, anchors, ct, bt, ctx.alpha, losses, grad[:3].contiguous().float())
+        return g[0], g[1], g[2], None, None, None, None
+
+
 def fcos_loss(cls_logits: Tensor, bbox_regression: Tensor, bbox_ctrness: Tensor, anchors: Tensor,
               cls_targets: Tensor, box_targets: Tensor, alpha: float = 0.25) -> Tensor:
     """fcos.py:149-202 fused: returns a device tensor [4] = classification, bbox_regression, bbox_ctrness
@@ -491,8 +549,11 @@ def fcos_loss(cls_logits: Tensor, bbox_regression: Tensor, bbox_ctrness: Tensor,
     if bbox_regression.shape != (B, N, 4) or bbox_ctrness.numel() != B * N or cls_targets.shape != (B, N):
         raise RuntimeError("fcos_loss: expected cls_logits [B,N,C], bbox_regression [B,N,4], bbox_ctrness [B,N,1], "
                            "cls_targets [B,N]")
-    return _fcos_loss_op(cls_logits.contiguous(), bbox_regression.contiguous(), bbox_ctrness.contiguous(),
-                         _f32c(anchors), cls_targets.contiguous(), _f32c(box_targets), float(alpha))
+    args = (cls_logits.contiguous(), bbox_regression.contiguous(), bbox_ctrness.contiguous(), _f32c(anchors),
+            cls_targets.contiguous(), _f32c(box_targets), float(alpha))
+    if torch.compiler.is_compiling():
+        return _fcos_loss_op(*args)
+    return _FcosLossFn.apply(*args)
 
 
 # --------------------------------------------------------------------------------- RoIAlign
@@ -649,14 +710,40 @@ def _msroi_backward(ctx, grad):
 _msroi_fwd_op.register_autograd(_msroi_backward, setup_context=_msroi_setup)
 
 
+class _MsroiAlignFn(torch.autograd.Function):
+    """Eager path of dgod_b200::msroi_align (same kernels, no dispatcher round trip)."""
+
+    @staticmethod
+    def forward(ctx, rois, roi_img_offsets, scales, ph, pw, sr, aligned, k_min, k_max, s0, lvl0, *feats):
+        out = _msroi_fwd_op._init_fn(list(feats), rois, roi_img_offsets, scales, ph, pw, sr, aligned, k_min, k_max, s0, lvl0)
+        f0 = feats[0]
+        ctx.save_for_backward(rois)
+        ctx.roi_img_offsets = roi_img_offsets
+        ctx.meta = ([f0.shape[0], f0.shape[1]] + [d for f in feats for d in (f.shape[2], f.shape[3])],
+                    (not f0.is_contiguous()) and f0.is_contiguous(memory_format=torch.channels_last),
+                    list(scales), ph, pw, sr, aligned, k_min, k_max, s0, lvl0)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        (rois,) = ctx.saved_tensors
+        shapes, nhwc, scales, ph, pw, sr, aligned, k_min, k_max, s0, lvl0 = ctx.meta
+        grads = _msroi_bwd_op._init_fn(grad, rois, ctx.roi_img_offsets, shapes, nhwc, scales, ph, pw, sr, aligned, k_min,
+                                       k_max, s0, lvl0, BACKWARD_ALGO)
+        return (None,) * 11 + tuple(grads)
+
+
 def multiscale_roi_align(feats: Sequence[Tensor], rois: Tensor, scales: Sequence[float], output_size,
                          sampling_ratio: int, k_min: int, k_max: int, canonical_scale: float = 224.0,
                          canonical_level: float = 4.0, aligned: bool = False,
                          roi_img_offsets: Optional[Tensor] = None) -> Tensor:
     """One-launch replacement of TV ops/poolers.py:147-227: `rois` is [K,5] (batch idx, xyxy)."""
     ph, pw = (output_size, output_size) if isinstance(output_size, int) else (int(output_size[0]), int(output_size[1]))
-    return _msroi_fwd_op(list(feats), rois, roi_img_offsets, [float(s) for s in scales], ph, pw, int(sampling_ratio), bool(aligned),
-                         int(k_min), int(k_max), float(canonical_scale), float(canonical_level))
+    if torch.compiler.is_compiling():
+        return _msroi_fwd_op(list(feats), rois, roi_img_offsets, [float(s) for s in scales], ph, pw, int(sampling_ratio),
+                             bool(aligned), int(k_min), int(k_max), float(canonical_scale), float(canonical_level))
+    return _MsroiAlignFn.apply(rois, roi_img_offsets, [float(s) for s in scales], ph, pw, int(sampling_ratio), bool(aligned),
+                               int(k_min), int(k_max), float(canonical_scale), float(canonical_level), *feats)
 
 
 def _convert_to_roi_format(boxes: Sequence[Tensor]) -> Tensor:
@@ -710,7 +797,7 @@ class _GRLayer(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_output):
-        return _grl_scale_op(grad_output, ctx.alpha), None
+        return _eager(_grl_scale_op)(grad_output, ctx.alpha), None
 
 
 def grad_reverse(x: Tensor, alpha: float = 0.1) -> Tensor:
