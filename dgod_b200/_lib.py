@@ -61,6 +61,8 @@ SIGNATURES = {
     "dgod_fcos_loss_workspace_bytes": (sz, [C.c_longlong]),
     "dgod_fcos_loss_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, sz, vp]),
     "dgod_fcos_loss_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp]),
+    "dgod_fcos_candidates": (i32, [vp, vp, vp, vp, i32, i32, vp, i32, i32, vp, f32, i32, vp, vp, vp, vp, vp, vp]),
+    "dgod_balanced_sample": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
     "dgod_nms_workspace_bytes": (sz, [i32, i32, i32]),
     "dgod_nms_batched": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, f64, i32, i32, vp, vp, vp, vp, sz, vp]),
     "dgod_rpn_workspace_bytes": (sz, [C.POINTER(RpnConfig)]),
@@ -77,6 +79,8 @@ SIGNATURES = {
     "dgod_grl_scale": (i32, [vp, vp, i64, f32, i32, vp]),
     "dgod_image_batch": (i32, [C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), i32, i32,
                                C.POINTER(f32), C.POINTER(f32), vp, i32, i32, vp]),
+    "dgod_image_batch_u8": (i32, [C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), i32, i32,
+                                  C.POINTER(f32), C.POINTER(f32), vp, i32, i32, vp]),
     "dgod_nchw_to_nhwc": (i32, [vp, vp, i32, i32, i32, i32, vp]),
 }
 

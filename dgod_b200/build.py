@@ -15,7 +15,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 OBJ_DIR = PKG_DIR / "build"
 LIB_PATH = PKG_DIR / "libdgod_b200.so"
-SOURCES = ["error.cu", "tmap.cu", "match.cu", "fcos.cu", "fcos_loss.cu", "nms.cu", "rpn.cu", "roi_align.cu",
+SOURCES = ["error.cu", "tmap.cu", "match.cu", "fcos.cu", "fcos_loss.cu", "fcos_post.cu", "sampler.cu", "nms.cu", "rpn.cu", "roi_align.cu",
            "roi_align_fast.cu", "roi_align_tma.cu", "roi_align_own.cu", "misc.cu", "transform.cu"]
 
 NVCC_FLAGS = [

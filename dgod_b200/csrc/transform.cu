@@ -17,7 +17,7 @@ namespace dgod {
 constexpr int kMaxBatchImages = 16;   // per launch (pointers and sizes travel as kernel parameters)
 
 struct ImageBatchParams {
-  const float* img[kMaxBatchImages];
+  const void* img[kMaxBatchImages];     // fp32 in [0,1], or uint8 in 0..255 (divided by 255 on load: DrivingDataset.py:53)
   int in_h[kMaxBatchImages], in_w[kMaxBatchImages], out_h[kMaxBatchImages], out_w[kMaxBatchImages];
   float mean[4], std[4];
   int channels, pad_h, pad_w;
@@ -25,6 +25,12 @@ struct ImageBatchParams {
 
 constexpr int kPxPerThread = 4;       // consecutive output pixels per thread: one 128-bit store per channel
 
+template <typename In> __device__ __forceinline__ float ld_px(const In* p);
+template <> __device__ __forceinline__ float ld_px<float>(const float* p) { return __ldg(p); }
+// the dataset's `image / 255.0` (DrivingDataset.py:53): one IEEE division of the byte value, bit-identical to the host's
+template <> __device__ __forceinline__ float ld_px<uint8_t>(const uint8_t* p) { return __fdiv_rn((float)__ldg(p), 255.f); }
+
+template <typename In>
 __global__ void __launch_bounds__(256)
 image_batch_kernel(const ImageBatchParams p, float* __restrict__ out, int first_image) {
   const int b = blockIdx.z, y = blockIdx.y;
@@ -53,18 +59,18 @@ image_batch_kernel(const ImageBatchParams p, float* __restrict__ out, int first_
     lx1[q] = fminf(fmaxf(fx - (float)x0[q], 0.f), 1.f);
     lx0[q] = 1.f - lx1[q];
   }
-  const float* src = p.img[b];
+  const In* src = reinterpret_cast<const In*>(p.img[b]);
   const size_t cstride_in = (size_t)ih * iw;
-  const float* r0 = src + (size_t)y0 * iw;
-  const float* r1 = src + (size_t)y1 * iw;
+  const In* r0 = src + (size_t)y0 * iw;
+  const In* r1 = src + (size_t)y1 * iw;
 #pragma unroll
   for (int c = 0; c < 4; ++c)
     if (c < p.channels) {
       float v[kPxPerThread][4];
 #pragma unroll
       for (int q = 0; q < kPxPerThread; ++q) {        // the 16 taps of this channel in flight before the first blend
-        v[q][0] = __ldg(r0 + c * cstride_in + x0[q]); v[q][1] = __ldg(r0 + c * cstride_in + x1[q]);
-        v[q][2] = __ldg(r1 + c * cstride_in + x0[q]); v[q][3] = __ldg(r1 + c * cstride_in + x1[q]);
+        v[q][0] = ld_px<In>(r0 + c * cstride_in + x0[q]); v[q][1] = ld_px<In>(r0 + c * cstride_in + x1[q]);
+        v[q][2] = ld_px<In>(r1 + c * cstride_in + x0[q]); v[q][3] = ld_px<In>(r1 + c * cstride_in + x1[q]);
       }
       const float m = p.mean[c], sd = p.std[c];
       float o[kPxPerThread];
@@ -84,9 +90,9 @@ image_batch_kernel(const ImageBatchParams p, float* __restrict__ out, int first_
 
 using namespace dgod;
 
-extern "C" int dgod_image_batch(const float* const* images, const int* in_h, const int* in_w, const int* out_h,
-                                const int* out_w, int n_img, int channels, const float* mean, const float* std,
-                                float* out, int pad_h, int pad_w, dgod_stream_t stream) {
+static int image_batch_impl(const void* const* images, bool u8, const int* in_h, const int* in_w, const int* out_h,
+                            const int* out_w, int n_img, int channels, const float* mean, const float* std,
+                            float* out, int pad_h, int pad_w, dgod_stream_t stream) {
   DGOD_REQUIRE(n_img >= 0 && channels >= 1 && channels <= 4 && pad_h > 0 && pad_w > 0, "dgod_image_batch: bad size");
   DGOD_REQUIRE(pad_w % 4 == 0 && ((uintptr_t)out & 15) == 0, "dgod_image_batch: pad_w must be a multiple of 4 and out 16-byte aligned");
   if (n_img == 0) return DGOD_OK;
@@ -109,8 +115,23 @@ extern "C" int dgod_image_batch(const float* const* images, const int* in_h, con
     }
     p.channels = channels; p.pad_h = pad_h; p.pad_w = pad_w;
     dim3 grid(cdiv(pad_w, 256 * kPxPerThread), pad_h, n);
-    image_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, out, first);
+    if (u8) image_batch_kernel<uint8_t><<<grid, 256, 0, (cudaStream_t)stream>>>(p, out, first);
+    else image_batch_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(p, out, first);
     DGOD_LAUNCHED();
   }
   return DGOD_OK;
+}
+
+extern "C" int dgod_image_batch(const float* const* images, const int* in_h, const int* in_w, const int* out_h,
+                                const int* out_w, int n_img, int channels, const float* mean, const float* std,
+                                float* out, int pad_h, int pad_w, dgod_stream_t stream) {
+  return image_batch_impl(reinterpret_cast<const void* const*>(images), false, in_h, in_w, out_h, out_w, n_img, channels, mean,
+                          std, out, pad_h, pad_w, stream);
+}
+
+extern "C" int dgod_image_batch_u8(const uint8_t* const* images, const int* in_h, const int* in_w, const int* out_h,
+                                   const int* out_w, int n_img, int channels, const float* mean, const float* std,
+                                   float* out, int pad_h, int pad_w, dgod_stream_t stream) {
+  return image_batch_impl(reinterpret_cast<const void* const*>(images), true, in_h, in_w, out_h, out_w, n_img, channels, mean,
+                          std, out, pad_h, pad_w, stream);
 }

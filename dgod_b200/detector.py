@@ -86,7 +86,9 @@ class BalancedSampler:
     Given labels [B,N] (>=1 positive, 0 negative, <0 ignored) picks a uniformly random subset of
     min(#pos, P) positives and min(#neg, S - #picked_pos) negatives per image, exactly like
     upstream's two `randperm`s, but returns index tensors of static shape plus validity masks.
-    `keys` ([B,N] uniform numbers) can be injected to force a selection (tests)."""
+    `keys` ([B,N] uniform numbers) can be injected to force a selection (tests).  On the device the selection is
+    `ops.balanced_sample` (csrc/sampler.cu, one launch per batch); the two-`topk` torch formulation below is the host
+    form of the same rule (CPU tests of the host logic)."""
 
     def __init__(self, batch_size_per_image: int, positive_fraction: float):
         self.batch_size_per_image = batch_size_per_image
@@ -96,6 +98,10 @@ class BalancedSampler:
         B, N = labels.shape
         if keys is None:
             keys = torch.rand((B, N), device=labels.device)
+        if labels.is_cuda:
+            # one launch for the batch: radix select of the smallest keys per class, survivors in ascending index
+            pos_idx, pos_valid, neg_idx, neg_valid, _ = ops.balanced_sample(labels, keys, self.num_pos, self.batch_size_per_image)
+            return pos_idx, pos_valid, neg_idx, neg_valid
         P, S = min(self.num_pos, N), min(self.batch_size_per_image, N)
         pk = torch.where(labels >= 1, keys, torch.full_like(keys, 2.0))
         nk = torch.where(labels == 0, keys, torch.full_like(keys, 2.0))

@@ -2,9 +2,11 @@
 plain nn.Module + explicit step function (pytorch_lightning is not a dependency of the hot path).
 
 Same heads, same 5-mode schedule (0,1,0,2,0,3,0,4), same per-image detector passes in modes 2-4,
-same optimizer (SGD lr 2e-3, wd 5e-4).  The gradient-reversal layers use the GRL kernel; for the
-instance-level heads, whose first layer is a Linear (DGFRCNN.py:8,19-20,29,40-41), the reversal
-scale is folded into that layer's input-gradient GEMM (ops.grl_linear).
+same optimizer (SGD lr 2e-3, wd 5e-4).  Every gradient-reversal layer is fused into the input-gradient
+of the layer behind it: the instance-level heads start with a Linear (DGFRCNN.py:8,19-20,29,40-41:
+ops.grl_linear, the scale is the GEMM's alpha), the image-level head with a Conv2d (DGcommon.py:53,73-74:
+ops.grl_conv2d, cuDNN's dgrad on the pre-scaled weight).  `ops.grad_reverse` (the stand-alone kernel)
+remains what `patch()` binds to the reference's own `grad_reverse` call sites.
 """
 from __future__ import annotations
 
@@ -35,8 +37,8 @@ class ImageDAFPN(nn.Module):
             nn.init.constant_(conv.bias, 0)
 
     def forward(self, x: Tensor) -> Tensor:
-        x = ops.grad_reverse(x)
-        for conv in (self.Conv1, self.Conv2, self.Conv3, self.Conv4):
+        x = F.relu(ops.grl_conv2d(x, self.Conv1))           # grad_reverse fused into Conv1's input gradient (DGcommon.py:73-74)
+        for conv in (self.Conv2, self.Conv3, self.Conv4):
             x = F.relu(conv(x))
         x = F.relu(self.linear1(x.flatten(1)))
         return torch.sigmoid(self.linear2(x))

@@ -9,7 +9,8 @@ per-location work of the path runs on the sm_100a kernels:
   * location -> GT assignment + target gather (fcos.py:510-548, 136-158): ONE `dgod_fcos_assign`
     launch per batch (rows A10/A11 of SURVEY.md §8a) instead of ~25 ATen kernels per image;
   * eval post-processing (fcos.py:552-619): `ops.clip_boxes_to_image` / `ops.batched_nms` (row A12);
-  * gradient reversal in front of the DG heads (DGcommon.py:33-45, row A13): `ops.grad_reverse`.
+  * gradient reversal in front of the DG heads (DGcommon.py:33-45, row A13): fused into the first layer's input gradient
+    (`ops.grl_conv2d` for ImageDA.Conv1, `ops.grl_linear` for the per-location heads).
 
 Names, arguments and the contents of the returned dicts follow the reference so that the parity
 tests read like its own code.
@@ -97,29 +98,26 @@ class FCOS(_TVFCOS):
         return self.head.compute_loss(targets, head_outputs, anchors, assigned)
 
     def postprocess_detections(self, head_outputs, anchors, image_shapes):
-        # fcos.py:552-619 with the NMS / clip kernels
+        """fcos.py:552-619 for the batch: candidates (score, threshold, top-k, decode, clip) of every image and level in ONE
+        launch, the per-class NMS of all images in ONE segmented call (vanilla mode; the reference switches to the
+        coordinate trick below 4 000 candidates, same keeps up to rounding-edge pairs), one device->host read for the
+        detection counts that TV's list-of-dicts result needs."""
         class_logits, box_regression, box_ctrness = (head_outputs["cls_logits"], head_outputs["bbox_regression"],
                                                      head_outputs["bbox_ctrness"])
+        npl = [a.shape[0] for a in anchors[0]]
+        cl, rg, ct = torch.cat(list(class_logits), dim=1), torch.cat(list(box_regression), dim=1), torch.cat(list(box_ctrness), dim=1)
+        dev = cl.device
+        sizes = ops.device_constant(tuple((float(h), float(w)) for h, w in image_shapes), torch.float32, dev)
+        boxes, scores, labels, valid, _ = ops.fcos_candidates(cl, rg, ct, torch.cat(list(anchors[0])), npl, sizes,
+                                                               self.score_thresh, self.topk_candidates)
+        B, per = boxes.shape[0], boxes.shape[1]
+        keep, info = ops.nms_segments(boxes.view(-1, 4), scores.view(-1), labels.view(-1), [per] * B, self.nms_thresh,
+                                      valid=valid.view(-1), max_out_per_seg=self.detections_per_img)
+        nums = info[:-1].tolist()
         detections: List[Dict[str, Tensor]] = []
-        for index in range(len(image_shapes)):
-            image_boxes, image_scores, image_labels = [], [], []
-            for br, cl, bc, anchors_per_level in zip(box_regression, class_logits, box_ctrness, anchors[index]):
-                logits_per_level, num_classes = cl[index], cl.shape[-1]
-                scores_per_level = torch.sqrt(torch.sigmoid(logits_per_level) * torch.sigmoid(bc[index])).flatten()
-                keep_idxs = scores_per_level > self.score_thresh
-                scores_per_level = scores_per_level[keep_idxs]
-                topk_idxs = torch.where(keep_idxs)[0]
-                num_topk = min(self.topk_candidates, topk_idxs.size(0))
-                scores_per_level, idxs = scores_per_level.topk(num_topk)
-                topk_idxs = topk_idxs[idxs]
-                anchor_idxs = torch.div(topk_idxs, num_classes, rounding_mode="floor")
-                boxes_per_level = self.box_coder.decode(br[index][anchor_idxs], anchors_per_level[anchor_idxs])
-                image_boxes.append(ops.clip_boxes_to_image(boxes_per_level, image_shapes[index]))
-                image_scores.append(scores_per_level)
-                image_labels.append(topk_idxs % num_classes)
-            image_boxes, image_scores, image_labels = torch.cat(image_boxes), torch.cat(image_scores), torch.cat(image_labels)
-            keep = ops.batched_nms(image_boxes, image_scores, image_labels, self.nms_thresh)[: self.detections_per_img]
-            detections.append({"boxes": image_boxes[keep], "scores": image_scores[keep], "labels": image_labels[keep]})
+        for i in range(B):
+            k = keep[i, :nums[i]]
+            detections.append({"boxes": boxes[i][k], "scores": scores[i][k], "labels": labels[i][k]})
         return detections
 
 
@@ -150,8 +148,7 @@ class ImageDA(nn.Module):
             torch.nn.init.constant_(conv.bias, 0)
 
     def forward(self, x: Tensor) -> Tensor:
-        x = ops.grad_reverse(x)
-        x = self.reLu(self.Conv1(x))
+        x = self.reLu(ops.grl_conv2d(x, self.Conv1))        # grad_reverse fused into Conv1's input gradient (DGcommon.py:106-107)
         x = self.reLu(self.Conv2(x))
         x = self.reLu(self.Conv3(x))
         x = self.reLu(self.linear1(self.flatten(x)))
@@ -168,8 +165,8 @@ class InstanceDA(nn.Module):
         self.classifer = nn.Linear(128, num_domains)
 
     def forward(self, x: Tensor) -> Tensor:
-        x = ops.grad_reverse(x)
-        return torch.sigmoid(self.classifer(self.dc_relu1(self.dc_ip1(x))))
+        x = ops.grl_linear(x, self.dc_ip1.weight, self.dc_ip1.bias)      # grad_reverse fused into dc_ip1's dgrad (DGFCOS.py:14-15)
+        return torch.sigmoid(self.classifer(self.dc_relu1(x)))
 
 
 class _InsCls(nn.Module):
@@ -186,8 +183,10 @@ class _InsCls(nn.Module):
 
     def forward(self, x: Tensor) -> Tensor:
         if self.reverse:
-            x = ops.grad_reverse(x)
-        x = self.dc_ip2(self.dc_relu1(self.dc_ip1(x)))
+            x = ops.grl_linear(x, self.dc_ip1.weight, self.dc_ip1.bias)  # DGFCOS.py:34-35
+        else:
+            x = self.dc_ip1(x)
+        x = self.dc_ip2(self.dc_relu1(x))
         return torch.sigmoid(self.classifer(x))
 
 

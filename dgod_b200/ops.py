@@ -373,17 +373,21 @@ def resized_shape(h: int, w: int, min_size: int, max_size: int) -> Tuple[int, in
 def image_batch(images: Sequence[Tensor], image_mean: Sequence[float], image_std: Sequence[float], min_size: int,
                 max_size: int, size_divisible: int = 32):
     """GeneralizedRCNNTransform.forward for the images of a batch (TV transform.py:102-153: normalize,
-    resize, batch_images) in one launch.  images: CUDA fp32 [C,H,W] tensors (sizes may differ).  Returns
-    (batched [B,C,H_pad,W_pad] NCHW tensor, [(h_i, w_i)] resized sizes) — what `ImageList` holds."""
+    resize, batch_images) in one launch.  images: CUDA fp32 [C,H,W] tensors (sizes may differ) — or uint8 tensors with
+    values 0..255, in which case the dataset's `image / 255.0` (DrivingDataset.py:53) happens on load inside the kernel
+    (bit-identical, a quarter of the host->device bytes).  Returns (batched [B,C,H_pad,W_pad] NCHW tensor,
+    [(h_i, w_i)] resized sizes) — what `ImageList` holds."""
     _need_cuda(*images)
     lib = _lib.load()
     n = len(images)
     if n == 0:
         raise RuntimeError("image_batch: empty batch")
     imgs = []
+    u8 = images[0].dtype == torch.uint8
     for im in images:
-        if im.dim() != 3 or im.dtype != torch.float32:
-            raise RuntimeError(f"image_batch: images are expected to be float32 [C, H, W] tensors, got {tuple(im.shape)} {im.dtype}")
+        if im.dim() != 3 or im.dtype != (torch.uint8 if u8 else torch.float32):
+            raise RuntimeError("image_batch: images are expected to be [C, H, W] tensors, all float32 or all uint8, got "
+                               f"{tuple(im.shape)} {im.dtype}")
         imgs.append(im.contiguous())
     Cn = imgs[0].shape[0]
     if Cn > 4 or Cn != len(image_mean) or Cn != len(image_std):
@@ -397,8 +401,8 @@ def image_batch(images: Sequence[Tensor], image_mean: Sequence[float], image_std
     ptrs = (C.c_void_p * n)(*[i.data_ptr() for i in imgs])
     ia = lambda v: (C.c_int * n)(*v)
     fa = lambda v: (C.c_float * Cn)(*[float(x) for x in v])
-    tok = KernelTimer.start("image_batch", sum(Cn * h * w * 4 for h, w in zip(in_h, in_w)) + out.numel() * 4)
-    check(lib.dgod_image_batch(ptrs, ia(in_h), ia(in_w), ia([s[0] for s in sizes]), ia([s[1] for s in sizes]), n, Cn,
+    tok = KernelTimer.start("image_batch", sum(Cn * h * w * (1 if u8 else 4) for h, w in zip(in_h, in_w)) + out.numel() * 4)
+    check((lib.dgod_image_batch_u8 if u8 else lib.dgod_image_batch)(ptrs, ia(in_h), ia(in_w), ia([s[0] for s in sizes]), ia([s[1] for s in sizes]), n, Cn,
                                fa(image_mean), fa(image_std), _p(out), pad_h, pad_w, _stream()))
     KernelTimer.stop(tok)
     return out, sizes
@@ -554,6 +558,37 @@ def fcos_loss(cls_logits: Tensor, bbox_regression: Tensor, bbox_ctrness: Tensor,
     if torch.compiler.is_compiling():
         return _fcos_loss_op(*args)
     return _FcosLossFn.apply(*args)
+
+
+def fcos_candidates(cls_logits: Tensor, bbox_regression: Tensor, bbox_ctrness: Tensor, anchors: Tensor,
+                    num_anchors_per_level: Sequence[int], image_sizes: Tensor, score_thresh: float = 0.2,
+                    topk: int = 1000):
+    """fcos.py:576-597 (FCOS.postprocess_detections up to the NMS) for the batch in one launch: cls_logits [B,N,C],
+    bbox_regression [B,N,4], bbox_ctrness [B,N,1] over all levels, anchors [N,4], image_sizes float [B,2] = (h, w) on the
+    device -> (boxes [B, L*topk, 4], scores [B, L*topk], labels int64 [B, L*topk], valid uint8 [B, L*topk],
+    counts int32 [B, L]); level l's survivors start at l*topk, in descending score.  No host synchronisation."""
+    _need_cuda(cls_logits, bbox_regression, bbox_ctrness, anchors, image_sizes)
+    lib = _lib.load()
+    cl, rg, ct, an = _f32c(cls_logits), _f32c(bbox_regression), _f32c(bbox_ctrness), _f32c(anchors)
+    B, N, Cn = cl.shape
+    if rg.shape != (B, N, 4) or ct.numel() != B * N or an.shape != (N, 4) or sum(num_anchors_per_level) != N:
+        raise RuntimeError("fcos_candidates: expected cls_logits [B,N,C], bbox_regression [B,N,4], bbox_ctrness [B,N,1], "
+                           "anchors [N,4] and num_anchors_per_level summing to N")
+    if not 1 <= int(topk) <= 1024:
+        raise RuntimeError("fcos_candidates: topk must be in 1..1024")
+    L, dev = len(num_anchors_per_level), cl.device
+    off = _offsets(num_anchors_per_level, dev)
+    boxes = torch.empty((B, L * topk, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((B, L * topk), dtype=torch.float32, device=dev)
+    labels = torch.empty((B, L * topk), dtype=torch.int64, device=dev)
+    valid = torch.empty((B, L * topk), dtype=torch.uint8, device=dev)
+    counts = torch.empty((B, L), dtype=torch.int32, device=dev)
+    tok = KernelTimer.start("fcos_candidates", B * N * (4 * Cn + 4) + B * L * topk * (16 + 16 + 16 + 4 + 8 + 1))
+    check(lib.dgod_fcos_candidates(_p(cl), _p(rg), _p(ct), _p(an), N, Cn, _p(off), L, B, _p(_f32c(image_sizes)),
+                                   float(score_thresh), int(topk), _p(boxes), _p(scores), _p(labels), _p(valid), _p(counts),
+                                   _stream()))
+    KernelTimer.stop(tok)
+    return boxes, scores, labels, valid, counts
 
 
 # --------------------------------------------------------------------------------- RoIAlign
@@ -834,6 +869,68 @@ class _GRLLinear(torch.autograd.Function):
 
 def grl_linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], alpha: float = 0.1) -> Tensor:
     return _GRLLinear.apply(x, weight, bias, alpha)
+
+
+class _GRLConv2d(torch.autograd.Function):
+    """grad_reverse followed by nn.Conv2d with the reversal scale folded into the convolution's input-gradient
+    (DGcommon.py:73-74 ImageDAFPN.Conv1, DGcommon.py:106-107 ImageDA.Conv1): cuDNN's dgrad runs on the weight
+    pre-scaled by -alpha — a pass over the 2-19 MB weight instead of a pass over the feature-map gradient
+    (637 MB for [8,256,152,256] fp32).  Weight and bias gradients use the unscaled operands."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, dilation, groups, alpha):
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (stride, padding, dilation, groups, alpha, None if bias is None else list(bias.shape))
+        return torch.nn.functional.conv2d(x, weight, bias, stride, padding, dilation, groups)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        stride, padding, dilation, groups, alpha, bias_sizes = ctx.cfg
+        gx = gw = gb = None
+        common = (list(stride), list(padding), list(dilation), False, [0, 0], groups)
+        if ctx.needs_input_grad[0]:
+            gx = torch.ops.aten.convolution_backward(gy, x, w * (-alpha), bias_sizes, *common, [True, False, False])[0]
+        if ctx.needs_input_grad[1] or (bias_sizes is not None and ctx.needs_input_grad[2]):
+            _, gw, gb = torch.ops.aten.convolution_backward(gy, x, w, bias_sizes, *common,
+                                                            [False, ctx.needs_input_grad[1], bias_sizes is not None])
+        return gx, gw, gb, None, None, None, None, None
+
+
+def grl_conv2d(x: Tensor, conv: "torch.nn.Conv2d", alpha: float = 0.1) -> Tensor:
+    """conv(grad_reverse(x)) for an nn.Conv2d with zeros padding, the reversal fused into the conv's dgrad."""
+    pad = conv.padding if not isinstance(conv.padding, str) else (0, 0)
+    if conv.padding_mode != "zeros" or isinstance(conv.padding, str):
+        return conv(grad_reverse(x, alpha))
+    return _GRLConv2d.apply(x, conv.weight, conv.bias, tuple(conv.stride), tuple(pad), tuple(conv.dilation), conv.groups, alpha)
+
+
+# --------------------------------------------------------------------------------- balanced sampler
+def balanced_sample(labels: Tensor, keys: Tensor, num_pos: int, batch_size_per_image: int):
+    """BalancedPositiveNegativeSampler (TV models/detection/_utils.py:11-71) for a batch in one launch: labels [B,N]
+    (float or int64: >= 1 positive, 0 negative, < 0 ignored), keys [B,N] uniform random floats.  Returns
+    (pos_idx [B,P'], pos_valid bool, neg_idx [B,S'], neg_valid bool, counts int32 [B,2]) with P' = min(num_pos, N),
+    S' = min(batch_size_per_image, N); indices ascending, zero past the counts.  No host synchronisation."""
+    _need_cuda(labels, keys)
+    if labels.dim() != 2 or keys.shape != labels.shape:
+        raise RuntimeError("balanced_sample: labels and keys must be [B, N]")
+    if labels.dtype not in (torch.float32, torch.int64):
+        labels = labels.to(torch.int64)
+    labels, keys = labels.contiguous(), _f32c(keys)
+    B, N = labels.shape
+    P, S = min(int(num_pos), N), min(int(batch_size_per_image), N)
+    dev = labels.device
+    pos_idx = torch.empty((B, P), dtype=torch.int64, device=dev)
+    neg_idx = torch.empty((B, S), dtype=torch.int64, device=dev)
+    pos_valid = torch.empty((B, P), dtype=torch.bool, device=dev)
+    neg_valid = torch.empty((B, S), dtype=torch.bool, device=dev)
+    counts = torch.empty((B, 2), dtype=torch.int32, device=dev)
+    tok = KernelTimer.start("balanced_sample", B * N * (labels.element_size() + 4) + B * (P + S) * 9)
+    check(_lib.load().dgod_balanced_sample(_p(labels), int(labels.dtype == torch.int64), _p(keys), B, N, int(num_pos),
+                                           int(batch_size_per_image), _p(pos_idx), _p(pos_valid), _p(neg_idx), _p(neg_valid),
+                                           _p(counts), _stream()))
+    KernelTimer.stop(tok)
+    return pos_idx, pos_valid, neg_idx, neg_valid, counts
 
 
 # --------------------------------------------------------------------------------- RPN

@@ -16,6 +16,8 @@
  *   dgod_iou_match          TV rpn.py:193-229 and TV roi_heads.py:580-613 (fasterrcnn.py:187,272)
  *   dgod_fcos_assign        fcos.py:510-548 and fcos.py:136-158
  *   dgod_fcos_loss_fwd/_bwd fcos.py:149-202 (focal + GIoU + centre-ness losses of FCOSHead.compute_loss)
+ *   dgod_fcos_candidates    fcos.py:576-597 (FCOS.postprocess_detections up to the NMS: score, threshold, top-k, decode, clip)
+ *   dgod_balanced_sample    TV models/detection/_utils.py:11-71 (BalancedPositiveNegativeSampler; fasterrcnn.py:119-123,272)
  *   dgod_nms_batched        TV ops/boxes.py:20-120 -> torchvision::nms (TV rpn.py:289,
  *                           TV roi_heads.py:728, fcos.py:608)
  *   dgod_rpn_proposals      fasterrcnn.py:174-182 -> TV _utils.py:162-224, TV rpn.py:231-297,
@@ -139,6 +141,33 @@ int dgod_fcos_loss_bwd(const float* cls_logits, const float* bbox_regression, co
                        const float* losses /*device [4] from the forward*/,
                        const float* grad_losses /*device [3]*/, float* grad_cls_logits,
                        float* grad_bbox_regression, float* grad_bbox_ctrness, dgod_stream_t stream);
+
+/* FCOS eval post-processing up to the NMS (fcos.py:576-597) for a batch in one launch: per
+ * image and level score = sqrt(sigmoid(cls) * sigmoid(ctrness)) over [locations x classes], `> score_thresh`, the topk
+ * (<= 1024) best in descending score (equal scores: ascending location * classes + class), BoxLinearCoder decode with
+ * normalize_by_size (fcos.py:72-100) and clip to the image.  Head outputs are the concatenated [n_img, n_anchors, ...]
+ * tensors (fp32, contiguous); level l owns anchors level_offsets[l] .. level_offsets[l+1] (device int32 [n_levels+1]).
+ * Outputs have fixed capacity [n_img, n_levels * topk] (boxes [..,4], scores, labels int64, valid uint8; rows past
+ * out_count[img * n_levels + l] are zero / invalid) so that dgod_nms_batched can run on them with its `valid` mask and
+ * n_levels * topk boxes per segment — no host synchronisation. */
+int dgod_fcos_candidates(const float* cls_logits, const float* bbox_regression, const float* bbox_ctrness,
+                         const float* anchors /*device [n_anchors,4]*/, int n_anchors, int num_classes,
+                         const int32_t* level_offsets /*device [n_levels+1]*/, int n_levels, int n_img,
+                         const float* image_sizes /*device [n_img,2] = (h, w)*/, float score_thresh, int topk,
+                         float* out_boxes, float* out_scores, int64_t* out_labels, uint8_t* out_valid,
+                         int32_t* out_count /*device [n_img * n_levels]*/, dgod_stream_t stream);
+
+/* ------------------------------------------------------------------ balanced sampler */
+
+/* BalancedPositiveNegativeSampler for a batch in one launch, no host synchronisation.  labels [n_img, n] (fp32 as the RPN
+ * produces them, or int64 as the RoI heads do): >= 1 positive, 0 negative, < 0 ignored.  keys [n_img, n] fp32: one
+ * uniform random number per candidate; per image the min(#pos, num_pos) positives and the min(#neg, batch - #picked_pos)
+ * negatives with the SMALLEST keys are selected (equal keys: ascending index) — a uniformly random subset like upstream's
+ * randperm.  Outputs: pos_idx [n_img, min(num_pos, n)], neg_idx [n_img, min(batch, n)] (int64, ascending index, zero past
+ * the count), pos_valid / neg_valid (uint8, same shapes), counts int32 [n_img, 2] = (#pos picked, #neg picked). */
+int dgod_balanced_sample(const void* labels, int labels_are_int64, const float* keys, int n_img, int n,
+                         int num_pos, int batch_size_per_image, int64_t* pos_idx, uint8_t* pos_valid,
+                         int64_t* neg_idx, uint8_t* neg_valid, int32_t* counts, dgod_stream_t stream);
 
 /* ------------------------------------------------------------------ batched NMS */
 
@@ -275,6 +304,12 @@ int dgod_detect_candidates(const float* class_logits /*[n_rows,n_cls]*/,
 int dgod_image_batch(const float* const* images, const int* in_h, const int* in_w, const int* out_h,
                      const int* out_w, int n_img, int channels, const float* mean, const float* std,
                      float* out, int pad_h, int pad_w, dgod_stream_t stream);
+/* The same for uint8 images [channels, in_h, in_w] with values 0..255, as they leave the decoder: every tap is divided by 255
+ * on load — the dataset's `image / 255.0` (DrivingDataset.py:53), bit-identical to doing it on the host — so that the
+ * host->device copy moves a quarter of the bytes. */
+int dgod_image_batch_u8(const uint8_t* const* images, const int* in_h, const int* in_w, const int* out_h,
+                        const int* out_w, int n_img, int channels, const float* mean, const float* std,
+                        float* out, int pad_h, int pad_w, dgod_stream_t stream);
 
 /* ------------------------------------------------------------------ layout */
 

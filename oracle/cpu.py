@@ -141,6 +141,38 @@ def fcos_loss(cls_logits, bbox_regression, bbox_ctrness, anchors, cls_targets, b
     return out
 
 
+def fcos_candidates(cls_logits, bbox_regression, bbox_ctrness, anchors, num_anchors_per_level, img_h, img_w,
+                    score_thresh=0.2, topk=1000):
+    """fcos.py:576-597 for one image: head outputs [N,C] / [N,4] / [N] over all levels -> (boxes [L*topk,4], scores,
+    labels int64, counts [L]); level l's survivors start at l*topk."""
+    cl, rg, ct = _f32(cls_logits), _f32(bbox_regression).reshape(-1, 4), _f32(bbox_ctrness).reshape(-1)
+    an = _f32(anchors).reshape(-1, 4)
+    off = np.zeros(len(num_anchors_per_level) + 1, np.int32)
+    off[1:] = np.cumsum(num_anchors_per_level)
+    L = len(num_anchors_per_level)
+    boxes = np.empty((L * topk, 4), np.float32)
+    scores = np.empty(L * topk, np.float32)
+    labels = np.empty(L * topk, np.int64)
+    counts = np.empty(L, np.int32)
+    lib().o_fcos_candidates(_p(cl), _p(rg), _p(ct), _p(an), C.c_int(cl.shape[1]), _p(off), C.c_int(L), C.c_float(img_h),
+                            C.c_float(img_w), C.c_float(score_thresh), C.c_int(topk), _p(boxes), _p(scores), _p(labels),
+                            _p(counts))
+    return boxes, scores, labels, counts
+
+
+def balanced_sample(labels, keys, num_pos, batch_size):
+    """BalancedPositiveNegativeSampler with explicit keys (TV models/detection/_utils.py:11-71): per image the
+    min(#pos, num_pos) positives and min(#neg, batch - #picked_pos) negatives with the smallest keys (ties: lower index),
+    returned as ascending index arrays."""
+    out = []
+    for lab, key in zip(np.asarray(labels), np.asarray(keys, dtype=np.float32)):
+        pos, neg = np.nonzero(lab >= 1)[0], np.nonzero(lab == 0)[0]
+        p = pos[np.lexsort((pos, key[pos]))][:num_pos]
+        n = neg[np.lexsort((neg, key[neg]))][:max(batch_size - len(p), 0)]
+        out.append((np.sort(p), np.sort(n)))
+    return out
+
+
 def image_batch(images, mean, std, min_size, max_size, size_divisible=32):
     """GeneralizedRCNNTransform.forward for a list of [C,H,W] images -> ([B,C,Hp,Wp] float32, [(h,w)])."""
     import math

@@ -9,6 +9,7 @@ Fixtures:
   frcnn_hotpath.npz   fasterrcnn.RegionProposalNetworkWILDS / RoIHeadsWILDS (fasterrcnn.py:90-305) on
                       synthetic FPN features: proposals, anchor labels, sampled RoI labels, pooled
                       features checksum, per-image losses
+  fcos_post.npz       fcos.FCOS.postprocess_detections (fcos.py:552-619) on seeded head outputs: eval detections
   fcos_loss.npz       fcos.FCOSHead.compute_loss (fcos.py:124-202) on seeded head outputs: losses and gradients
   fcos_step.npz       losses + gt_classes of one training forward of fcos.fcos_resnet50_fpn with name-seeded
                       weights (the dgod_b200.dg_fcos mirror must reproduce them on the GPU)
@@ -114,6 +115,34 @@ def gen_fcos_loss(fcos):
                         grad_cls=ho["cls_logits"].grad.numpy(), grad_reg=ho["bbox_regression"].grad.numpy(),
                         grad_ctr=ho["bbox_ctrness"].grad.numpy())
     print("fcos_loss.npz", {k: float(loss[k]) for k in ("classification", "bbox_regression", "bbox_ctrness")})
+
+
+def fcos_post_inputs():
+    """Seeded head outputs for the eval post-processing on the anchors of fcos_inputs(): 3 images, class logits around the
+    0.2 score threshold (so that the threshold, the top-k cut and the NMS all bite), positive box regressions."""
+    anchors, npl, _, _ = fcos_inputs()
+    B, N = 3, len(anchors)
+    g = synth.gen(777)
+    return {"cls_logits": torch.randn(B, N, 9, generator=g) * 2.5 - 2.0,
+            "bbox_regression": torch.rand(B, N, 4, generator=g) * 3.0 + 0.1,
+            "bbox_ctrness": torch.randn(B, N, 1, generator=g) * 1.5}, [(256, 320), (250, 300), (256, 320)]
+
+
+def gen_fcos_post(fcos):
+    """fcos.FCOS.postprocess_detections (fcos.py:552-619) on seeded head outputs, topk_candidates lowered to 300 so that
+    the top-k cut is exercised: detections per image."""
+    anchors, npl, _, _ = fcos_inputs()
+    ho, shapes = fcos_post_inputs()
+    a = torch.from_numpy(anchors)
+    stub = types.SimpleNamespace(score_thresh=0.2, nms_thresh=0.6, detections_per_img=100, topk_candidates=300,
+                                 box_coder=fcos.BoxLinearCoder(normalize_by_size=True))
+    split = {k: list(v.split(npl, dim=1)) for k, v in ho.items()}
+    det = fcos.FCOS.postprocess_detections(stub, split, [list(a.split(npl))] * len(shapes), shapes)
+    out = {}
+    for i, d in enumerate(det):
+        out[f"boxes{i}"], out[f"scores{i}"], out[f"labels{i}"] = d["boxes"].numpy(), d["scores"].numpy(), d["labels"].numpy()
+    np.savez_compressed(OUT / "fcos_post.npz", **out)
+    print("fcos_post.npz", [len(d["boxes"]) for d in det])
 
 
 # ----------------------------------------------------------------------------------------- Faster R-CNN hot path
@@ -261,6 +290,7 @@ def main():
     fasterrcnn, fcos = import_reference()
     gen_fcos(fcos)
     gen_fcos_loss(fcos)
+    gen_fcos_post(fcos)
     gen_fcos_step(fcos)
     gen_hotpath(fasterrcnn)
     gen_step(fasterrcnn)

@@ -80,6 +80,9 @@ def test_batched_nms_large_properties(n):
     scores = synth.distinct_scores(n, g).to(DEV)
     idxs = torch.randint(0, 5, (n,), generator=g).to(DEV)
     keep = ops.batched_nms(boxes, scores, idxs, 0.7)
+    # bit-exact against the C oracle (torchvision's CPU arithmetic: fp32 IoU compared in double) at the full size
+    ref = O.batched_nms(boxes.cpu().numpy(), scores.cpu().numpy(), idxs.cpu().numpy(), 0.7, mode=0)
+    assert np.array_equal(keep.cpu().numpy(), ref)
     ks = scores[keep]
     assert keep.dtype == torch.int64 and len(torch.unique(keep)) == len(keep)
     assert bool((ks[:-1] > ks[1:]).all())                                        # descending score

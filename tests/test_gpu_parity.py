@@ -490,6 +490,105 @@ def test_grl_linear_matches_unfused():
     torch.testing.assert_close(gw1, lin.weight.grad, rtol=1e-5, atol=1e-5)
 
 
+def test_fcos_eval_candidates_kernel():
+    """ops.fcos_candidates (fcos.py:576-597 in one launch) against the C oracle and, with the segmented NMS behind it,
+    against the detections of the reference's own FCOS.postprocess_detections (tests/golden/fcos_post.npz)."""
+    from pathlib import Path
+    from oracle import gen_golden as G
+    ops = _ops()
+    gold = np.load(Path(__file__).parent / "golden" / "fcos_post.npz")
+    anchors, npl, _, _ = G.fcos_inputs()
+    ho, shapes = G.fcos_post_inputs()
+    sizes = torch.tensor([[float(h), float(w)] for h, w in shapes], device=DEV)
+    topk = 300
+    boxes, scores, labels, valid, counts = ops.fcos_candidates(ho["cls_logits"].to(DEV), ho["bbox_regression"].to(DEV),
+                                                                ho["bbox_ctrness"].to(DEV), torch.from_numpy(anchors).to(DEV),
+                                                                npl, sizes, 0.2, topk)
+    L = len(npl)
+    for i, (h, w) in enumerate(shapes):
+        rb, rs, rl, rc = O.fcos_candidates(ho["cls_logits"][i].numpy(), ho["bbox_regression"][i].numpy(),
+                                           ho["bbox_ctrness"][i].numpy(), anchors, npl, h, w, 0.2, topk)
+        assert np.array_equal(counts[i].cpu().numpy(), rc)
+        assert np.array_equal(valid[i].cpu().numpy().reshape(L, topk), np.arange(topk)[None, :] < rc[:, None])
+        got_s, got_l, got_b = scores[i].cpu().numpy(), labels[i].cpu().numpy(), boxes[i].cpu().numpy()
+        np.testing.assert_allclose(got_s, rs, rtol=1e-6)                         # expf: scores to ~1 ulp
+        same = got_l == rl                                                        # order can differ only where scores are 1 ulp apart
+        assert same.mean() > 0.995
+        assert np.array_equal(got_b[same], rb[same])
+    per = L * topk
+    keep, info = ops.nms_segments(boxes.view(-1, 4), scores.view(-1), labels.view(-1), [per] * len(shapes), 0.6,
+                                  valid=valid.view(-1), max_out_per_seg=100)
+    nums = info[:-1].tolist()
+    for i in range(len(shapes)):
+        k = keep[i, :nums[i]]
+        assert nums[i] == len(gold[f"labels{i}"])
+        assert np.array_equal(labels[i][k].cpu().numpy(), gold[f"labels{i}"])
+        np.testing.assert_allclose(scores[i][k].cpu().numpy(), gold[f"scores{i}"], rtol=1e-6)
+        np.testing.assert_allclose(boxes[i][k].cpu().numpy(), gold[f"boxes{i}"], rtol=0, atol=1e-4)
+    # degenerate inputs: nothing passes the threshold; threshold 0 with fewer elements than topk
+    none = ops.fcos_candidates(torch.full((1, len(anchors), 9), -20.0, device=DEV), ho["bbox_regression"][:1].to(DEV),
+                               ho["bbox_ctrness"][:1].to(DEV), torch.from_numpy(anchors).to(DEV), npl, sizes[:1], 0.2, topk)
+    assert int(none[4].sum()) == 0 and int(none[3].sum()) == 0 and float(none[0].abs().sum()) == 0.0
+    few = ops.fcos_candidates(ho["cls_logits"][:1].to(DEV), ho["bbox_regression"][:1].to(DEV), ho["bbox_ctrness"][:1].to(DEV),
+                              torch.from_numpy(anchors).to(DEV), npl, sizes[:1], 0.0, 1000)
+    assert few[4][0].cpu().tolist() == [min(1000, 9 * n) for n in npl]
+
+
+@pytest.mark.parametrize("n,dtype", [(155520, torch.float32), (2020, torch.int64), (300, torch.int64), (40, torch.float32)])
+def test_balanced_sampler_kernel(n, dtype):
+    """ops.balanced_sample (TV _utils.py:11-71 with explicit keys) against the numpy oracle: bit-exact index lists, incl.
+    images with fewer positives / negatives than asked for, no positives at all, massive key ties, and N < batch."""
+    ops = _ops()
+    g = synth.gen(n)
+    B = 5
+    lab = torch.full((B, n), -1.0)
+    r = torch.rand(B, n, generator=g)
+    lab[r < 0.6] = 0.0
+    lab[r < 0.01] = 1.0                       # ~1 % positives
+    lab[1][lab[1] == 1] = 0.0                 # image 1: no positives
+    lab[2][:] = -1.0
+    lab[2][: min(n, 37)] = 1.0                # image 2: 37 positives, no negatives
+    lab[3][lab[3] == 0] = -1.0                # image 3: no negatives
+    keys = torch.rand(B, n, generator=g)
+    keys[4] = (keys[4] * 4).floor() / 4       # image 4: only 4 distinct keys -> ties decide
+    labels = lab.to(dtype) * (3 if dtype == torch.int64 else 1)
+    P, S = (128, 256) if dtype == torch.float32 else (128, 512)
+    pi, pv, ni, nv, cnt = ops.balanced_sample(labels.to(DEV), keys.to(DEV), P, S)
+    ref = O.balanced_sample(lab.numpy(), keys.numpy(), P, S)
+    for b, (rp, rn) in enumerate(ref):
+        assert cnt[b].tolist() == [len(rp), len(rn)]
+        assert np.array_equal(pi[b, :len(rp)].cpu().numpy(), rp) and np.array_equal(ni[b, :len(rn)].cpu().numpy(), rn)
+        assert pv[b].cpu().numpy().tolist() == [i < len(rp) for i in range(pi.shape[1])]
+        assert nv[b].cpu().numpy().tolist() == [i < len(rn) for i in range(ni.shape[1])]
+    assert pi.shape == (B, min(P, n)) and ni.shape == (B, min(S, n))
+
+
+def test_grl_conv2d_matches_unfused():
+    """ops.grl_conv2d (the reversal folded into cuDNN's dgrad, DGcommon.py:73-74,106-107) against conv(grad_reverse(x))
+    with the stand-alone GRL kernel: same output, input gradient to fp32 rounding, weight / bias gradients identical."""
+    ops = _ops()
+    g = synth.gen(13)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for cin, cout, stride, shape in [(256, 256, (2, 4), (2, 256, 38, 64)), (64, 32, 2, (1, 64, 19, 32))]:
+            conv = torch.nn.Conv2d(cin, cout, 3, stride=stride).to(DEV)
+            x = torch.randn(*shape, generator=g).to(DEV).requires_grad_(True)
+            y1 = ops.grl_conv2d(x, conv)
+            go = torch.randn(y1.shape, generator=g).to(DEV)
+            y1.backward(go)
+            g1, gw1, gb1 = x.grad.clone(), conv.weight.grad.clone(), conv.bias.grad.clone()
+            x.grad = conv.weight.grad = conv.bias.grad = None
+            y2 = conv(ops.grad_reverse(x))
+            y2.backward(go)
+            assert torch.equal(y1, y2)
+            torch.testing.assert_close(g1, x.grad, rtol=1e-5, atol=1e-6 * float(x.grad.abs().max()))
+            torch.testing.assert_close(gw1, conv.weight.grad, rtol=1e-5, atol=1e-5)
+            torch.testing.assert_close(gb1, conv.bias.grad, rtol=1e-5, atol=1e-5)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 # ------------------------------------------------------------------------------- FCOS loss tail
 def test_fcos_loss_tail_forward_backward():
     """ops.fcos_loss (fcos.py:149-202 fused) against the golden losses AND gradients produced by the reference's
@@ -551,6 +650,27 @@ def test_image_batch_and_fused_transform():
             assert torch.equal(targets[0]["boxes"], boxes[0].to(DEV))            # the caller's targets are not modified
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.image_batch(imgs, [0.0] * 3, [1.0] * 3, 150, 300)
+
+
+def test_image_batch_uint8_input():
+    """uint8 images (0..255, as the decoder yields them): the `/ 255.0` of DrivingDataset.py:53 happens on load inside the
+    kernel — bit-identical to dividing on the host and feeding floats, a quarter of the host->device bytes."""
+    from dgod_b200.detector import FusedTransform
+    ops = _ops()
+    g = synth.gen(22)
+    u8 = [torch.randint(0, 256, (3, h, w), generator=g, dtype=torch.uint8) for h, w in [(200, 333), (150, 400), (97, 101)]]
+    as_float = [(i / 255.0).float() for i in u8]                  # what the reference's dataset hands on
+    for (mn, mx, mean, std) in [(150, 300, [0.0, 0.0, 0.0], [1.0, 1.0, 1.0]), (224, 260, [0.485, 0.456, 0.406], [0.229, 0.224, 0.225])]:
+        a, sa = ops.image_batch([i.to(DEV) for i in u8], mean, std, mn, mx)
+        b, sb = ops.image_batch([i.to(DEV) for i in as_float], mean, std, mn, mx)
+        assert sa == sb and torch.equal(a, b)
+        ref, _ = O.image_batch([i.numpy() for i in as_float], mean, std, mn, mx)
+        np.testing.assert_allclose(a.cpu().numpy(), ref, rtol=0, atol=1e-6)
+    il, _ = FusedTransform(150, 300, [0.0] * 3, [1.0] * 3).to(DEV).eval()([i.to(DEV) for i in u8])
+    il2, _ = FusedTransform(150, 300, [0.0] * 3, [1.0] * 3).to(DEV).eval()([i.to(DEV) for i in as_float])
+    assert torch.equal(il.tensors, il2.tensors)
+    with pytest.raises(RuntimeError, match="all float32 or all uint8"):
+        ops.image_batch([u8[0].to(DEV), as_float[1].to(DEV)], [0.0] * 3, [1.0] * 3, 150, 300)
 
 
 def test_image_batch_more_images_than_one_launch_takes():

@@ -42,6 +42,23 @@ def test_fcos_loss_tail_matches_reference():
     assert out[3] == sum(int((c >= 0).sum()) for c in cls_t) > 0
 
 
+def test_fcos_eval_candidates_and_nms_match_reference():
+    """oracle o_fcos_candidates + batched_nms == fcos.FCOS.postprocess_detections of the reference (fcos.py:552-619) on
+    seeded head outputs: labels identical, boxes identical, scores to 1 ulp (expf inside the sigmoid)."""
+    gold = np.load(GOLD / "fcos_post.npz")
+    anchors, npl, _, _ = G.fcos_inputs()
+    ho, shapes = G.fcos_post_inputs()
+    for i, (h, w) in enumerate(shapes):
+        b, s, l, c = O.fcos_candidates(ho["cls_logits"][i].numpy(), ho["bbox_regression"][i].numpy(),
+                                       ho["bbox_ctrness"][i].numpy(), anchors, npl, h, w, 0.2, 300)
+        assert c.max() == 300 and c.min() < 300                                   # both the top-k cut and the threshold bite
+        v = np.concatenate([np.arange(k) + j * 300 for j, k in enumerate(c)])
+        keep = O.batched_nms(b[v], s[v], l[v], 0.6)[:100]
+        assert np.array_equal(l[v][keep], gold[f"labels{i}"])
+        assert np.array_equal(b[v][keep], gold[f"boxes{i}"])
+        np.testing.assert_allclose(s[v][keep], gold[f"scores{i}"], rtol=2e-7)
+
+
 class _Prefixed(nn.Module):
     """Gives sub-modules the attribute names they have inside the reference's containers so that
     gen_golden.seeded_module_weights draws identical weights."""
@@ -142,11 +159,12 @@ def test_fixtures_are_current():
             G.gen_fcos(fcos)
             G.gen_fcos_step(fcos)
             G.gen_fcos_loss(fcos)
+            G.gen_fcos_post(fcos)
             G.gen_hotpath(fasterrcnn)
             G.gen_step(fasterrcnn)
         finally:
             G.OUT = old
-        for name in ("fcos_assign.npz", "fcos_step.npz", "fcos_loss.npz", "frcnn_hotpath.npz", "frcnn_step.npz"):
+        for name in ("fcos_assign.npz", "fcos_step.npz", "fcos_loss.npz", "fcos_post.npz", "frcnn_hotpath.npz", "frcnn_step.npz"):
             a, b = np.load(Path(d) / name), np.load(GOLD / name)
             for k in b.files:
                 assert np.array_equal(a[k], b[k]), (name, k)
