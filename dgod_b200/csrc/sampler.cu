@@ -29,94 +29,28 @@ template <> __device__ __forceinline__ int label_class<int64_t>(const int64_t* _
   return v >= 1 ? 1 : (v == 0 ? 0 : -1);
 }
 
+constexpr int kSampUnroll = 4;          // independent (label, key) loads in flight per thread
+constexpr int kSampMaxList = 1024;      // survivors of both classes per image handled by the in-shared-memory sort
+
 struct SampShared {
-  unsigned hist[256];
+  unsigned hist[2][256];                // [class][digit]
   unsigned warp[kSampThreads / 32];
-  unsigned prefix, remaining, total, base_above, base_eq;
+  unsigned prefix[2], remaining[2], total[2], n_equal[2];
+  unsigned base_below[2], base_eq[2];
+  unsigned n_list;
+  int list[kSampMaxList];               // (index << 1) | class of the survivors, any order, then sorted
 };
 
-// The `want` smallest keys among the elements of class `cls` of one image -> out_idx (ascending index), out_valid.
-// Returns (to every thread) how many were selected.
+// class (1 positive, 0 negative, -1 ignored) and order-preserving key bits of element e
 template <typename L>
-__device__ unsigned select_class(const L* __restrict__ labels, const float* __restrict__ keys, int n, int cls, unsigned want,
-                                 int capacity, int64_t* __restrict__ out_idx, uint8_t* __restrict__ out_valid, SampShared& sh) {
-  const int tid = threadIdx.x;
-  unsigned prefix = 0, mask = 0, k = 0;
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 24 - 8 * pass;
-    for (int i = tid; i < 256; i += kSampThreads) sh.hist[i] = 0;
-    __syncthreads();
-    for (int e = tid; e < n; e += kSampThreads) {
-      if (label_class<L>(labels, e) == cls) {
-        const unsigned key = float_ordered(__ldg(keys + e));
-        if ((key & mask) == prefix) atomicAdd(&sh.hist[(key >> shift) & 255u], 1u);
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      if (pass == 0) {
-        unsigned total = 0;
-        for (int b = 0; b < 256; ++b) total += sh.hist[b];
-        sh.total = total;
-        sh.remaining = min(want, total);
-      }
-      unsigned rem = sh.remaining, b = 0;
-      if (rem > 0) {
-        for (; b < 255; ++b) {
-          if (sh.hist[b] >= rem) break;
-          rem -= sh.hist[b];
-        }
-      }
-      sh.prefix = prefix | (b << shift);
-      sh.remaining = rem;
-    }
-    __syncthreads();
-    if (pass == 0) k = min(want, sh.total);
-    prefix = sh.prefix;
-    mask |= 255u << shift;
-    if (k == 0) break;
-    __syncthreads();
+__device__ __forceinline__ void load_elem(const L* __restrict__ labels, const float* __restrict__ keys, int e, int n, int& cls,
+                                          unsigned& key) {
+  cls = -1;
+  key = 0;
+  if (e < n) {
+    cls = label_class<L>(labels, e);
+    key = float_ordered(__ldg(keys + e));
   }
-  const unsigned kth = prefix, n_eq = sh.remaining;      // key of the k-th smallest; n_eq of the equals are taken
-  __syncthreads();
-  if (tid == 0) { sh.base_above = 0; sh.base_eq = 0; }
-  __syncthreads();
-  // ordered compaction: every element below the k-th key, the first n_eq equal ones, in ascending index
-  for (int e0 = 0; e0 < n && k > 0; e0 += kSampThreads) {
-    const int e = e0 + tid;
-    bool below = false, eq = false;
-    if (e < n && label_class<L>(labels, e) == cls) {
-      const unsigned key = float_ordered(__ldg(keys + e));
-      below = key < kth;
-      eq = key == kth;
-    }
-    const unsigned bal_b = __ballot_sync(0xffffffffu, below), bal_e = __ballot_sync(0xffffffffu, eq);
-    if ((tid & 31) == 0) sh.warp[tid >> 5] = __popc(bal_b) | (__popc(bal_e) << 16);
-    __syncthreads();
-    unsigned before_b = 0, before_e = 0;
-    for (int w = 0; w < (tid >> 5); ++w) { before_b += sh.warp[w] & 0xffffu; before_e += sh.warp[w] >> 16; }
-    const unsigned lane_lt = (1u << (tid & 31)) - 1u;
-    const unsigned eq_rank = sh.base_eq + before_e + __popc(bal_e & lane_lt);
-    const bool take = below || (eq && eq_rank < n_eq);
-    // position = (#taken before this element): below-count so far + min(eq-count so far, n_eq)
-    const unsigned below_before = sh.base_above + before_b + __popc(bal_b & lane_lt);
-    const unsigned eq_before = min(eq_rank, n_eq);
-    if (take) {
-      const unsigned pos = below_before + eq_before;
-      if ((int)pos < capacity) { out_idx[pos] = e; out_valid[pos] = 1; }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      unsigned tb = 0, te = 0;
-      for (int w = 0; w < kSampThreads / 32; ++w) { tb += sh.warp[w] & 0xffffu; te += sh.warp[w] >> 16; }
-      sh.base_above += tb;
-      sh.base_eq += te;
-    }
-    __syncthreads();
-  }
-  for (int i = (int)k + tid; i < capacity; i += kSampThreads) { out_idx[i] = 0; out_valid[i] = 0; }
-  __syncthreads();
-  return k;
 }
 
 template <typename L>
@@ -125,15 +59,146 @@ balanced_sample_kernel(const L* __restrict__ labels, const float* __restrict__ k
                        int cap_pos, int cap_neg, int64_t* __restrict__ pos_idx, uint8_t* __restrict__ pos_valid,
                        int64_t* __restrict__ neg_idx, uint8_t* __restrict__ neg_valid, int32_t* __restrict__ counts) {
   __shared__ SampShared sh;
-  const int img = blockIdx.x;
+  const int img = blockIdx.x, tid = threadIdx.x;
   labels += (size_t)img * n;
   keys += (size_t)img * n;
-  // TV _utils.py:44-50: num_pos = min(#pos, batch * fraction); num_neg = min(#neg, batch - num_pos)
-  const unsigned np = select_class<L>(labels, keys, n, 1, (unsigned)num_pos, cap_pos, pos_idx + (size_t)img * cap_pos,
-                                      pos_valid + (size_t)img * cap_pos, sh);
-  const unsigned nn = select_class<L>(labels, keys, n, 0, (unsigned)batch_size - np, cap_neg, neg_idx + (size_t)img * cap_neg,
-                                      neg_valid + (size_t)img * cap_neg, sh);
-  if (threadIdx.x == 0) { counts[2 * img] = (int)np; counts[2 * img + 1] = (int)nn; }
+  int64_t* out_idx[2] = {neg_idx + (size_t)img * cap_neg, pos_idx + (size_t)img * cap_pos};
+  uint8_t* out_valid[2] = {neg_valid + (size_t)img * cap_neg, pos_valid + (size_t)img * cap_pos};
+  const int cap[2] = {cap_neg, cap_pos};
+
+  // ---- 4-pass radix select of the k-th smallest key of BOTH classes at once (class 1 = positives, 0 = negatives)
+  unsigned prefix[2] = {0, 0}, mask = 0, k[2] = {0, 0};
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = tid; i < 512; i += kSampThreads) (&sh.hist[0][0])[i] = 0;
+    __syncthreads();
+    for (int e0 = tid; e0 < n; e0 += kSampThreads * kSampUnroll) {
+      int cls[kSampUnroll];
+      unsigned key[kSampUnroll];
+#pragma unroll
+      for (int u = 0; u < kSampUnroll; ++u) load_elem<L>(labels, keys, e0 + u * kSampThreads, n, cls[u], key[u]);
+#pragma unroll
+      for (int u = 0; u < kSampUnroll; ++u)
+        if (cls[u] >= 0 && (key[u] & mask) == (cls[u] ? prefix[1] : prefix[0]) && (pass == 0 || (cls[u] ? k[1] : k[0]) > 0))
+          atomicAdd(&sh.hist[cls[u]][(key[u] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid < 2) {
+      const int c = tid;
+      if (pass == 0) {
+        unsigned total = 0;
+        for (int b = 0; b < 256; ++b) total += sh.hist[c][b];
+        sh.total[c] = total;
+      }
+    }
+    __syncthreads();
+    if (tid < 2) {
+      const int c = tid;
+      if (pass == 0) {
+        // TV _utils.py:44-50: num_pos = min(#pos, batch * fraction); num_neg = min(#neg, batch - num_pos)
+        const unsigned np = min((unsigned)num_pos, sh.total[1]);
+        sh.remaining[c] = c == 1 ? np : min((unsigned)batch_size - np, sh.total[0]);
+      }
+      unsigned rem = sh.remaining[c], b = 0;
+      if (rem > 0) {
+        for (; b < 255; ++b) {
+          if (sh.hist[c][b] >= rem) break;
+          rem -= sh.hist[c][b];
+        }
+      }
+      sh.prefix[c] = prefix[c] | (b << shift);
+      sh.remaining[c] = rem;
+      if (pass == 3) sh.n_equal[c] = sh.hist[c][b];      // elements whose key IS the k-th key
+    }
+    __syncthreads();
+    if (pass == 0) {
+      const unsigned np = min((unsigned)num_pos, sh.total[1]);
+      k[1] = np;
+      k[0] = min((unsigned)batch_size - np, sh.total[0]);
+    }
+    prefix[0] = sh.prefix[0]; prefix[1] = sh.prefix[1];
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  const unsigned kth[2] = {prefix[0], prefix[1]};
+  const unsigned n_eq[2] = {sh.remaining[0], sh.remaining[1]};      // how many of the equals are taken
+  const bool ties_cut[2] = {k[0] > 0 && sh.n_equal[0] != n_eq[0], k[1] > 0 && sh.n_equal[1] != n_eq[1]};
+  if (tid == 0) { sh.n_list = 0; sh.base_below[0] = sh.base_below[1] = sh.base_eq[0] = sh.base_eq[1] = 0; }
+  __syncthreads();
+
+  if (!ties_cut[0] && !ties_cut[1] && k[0] + k[1] <= (unsigned)kSampMaxList) {
+    // ---- common case (distinct keys at the cut): one pass gathers everything <= the k-th key of its class, then the short
+    // list is sorted by (class, index) in shared memory
+    for (int e0 = tid; e0 < n; e0 += kSampThreads * kSampUnroll) {
+      int cls[kSampUnroll];
+      unsigned key[kSampUnroll];
+#pragma unroll
+      for (int u = 0; u < kSampUnroll; ++u) load_elem<L>(labels, keys, e0 + u * kSampThreads, n, cls[u], key[u]);
+#pragma unroll
+      for (int u = 0; u < kSampUnroll; ++u)
+        if (cls[u] >= 0 && (cls[u] ? k[1] : k[0]) > 0 && key[u] <= (cls[u] ? kth[1] : kth[0]))
+          sh.list[atomicAdd(&sh.n_list, 1u)] = ((e0 + u * kSampThreads) << 1) | cls[u];
+    }
+    __syncthreads();
+    const unsigned m = sh.n_list;                          // == k[0] + k[1]
+    for (int i = (int)m + tid; i < kSampMaxList; i += kSampThreads) sh.list[i] = 0x7fffffff;
+    __syncthreads();
+    // sort key: class-major (negatives first), then index: value = (class << 30) | index  (n < 2^30)
+    for (int i = tid; i < (int)m; i += kSampThreads) sh.list[i] = ((sh.list[i] & 1) << 30) | (sh.list[i] >> 1);
+    __syncthreads();
+    for (int size = 2; size <= kSampMaxList; size <<= 1)
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const int i = tid, j = i ^ stride;
+        if (j > i) {
+          const bool up = (i & size) == 0;
+          const int a = sh.list[i], b = sh.list[j];
+          if ((a > b) == up) { sh.list[i] = b; sh.list[j] = a; }
+        }
+        __syncthreads();
+      }
+    for (int i = tid; i < (int)m; i += kSampThreads) {
+      const int v = sh.list[i], c = v >> 30, e = v & 0x3fffffff;
+      const int pos = c == 0 ? i : i - (int)k[0];
+      int64_t* oi = c ? out_idx[1] : out_idx[0];
+      uint8_t* ov = c ? out_valid[1] : out_valid[0];
+      if (pos < (c ? cap_pos : cap_neg)) { oi[pos] = e; ov[pos] = 1; }
+    }
+  } else {
+    // ---- equal keys at the cut (or more survivors than the list holds): ordered compaction, chunk by chunk — everything
+    // below the k-th key of its class, and the first n_eq equal ones, land in ascending index order
+    for (int c = 0; c < 2; ++c) {
+      if (k[c] == 0) continue;
+      for (int e0 = 0; e0 < n; e0 += kSampThreads) {
+        const int e = e0 + tid;
+        int cls;
+        unsigned key;
+        load_elem<L>(labels, keys, e, n, cls, key);
+        const bool below = cls == c && key < kth[c], eq = cls == c && key == kth[c];
+        const unsigned bal_b = __ballot_sync(0xffffffffu, below), bal_e = __ballot_sync(0xffffffffu, eq);
+        if ((tid & 31) == 0) sh.warp[tid >> 5] = __popc(bal_b) | (__popc(bal_e) << 16);
+        __syncthreads();
+        unsigned before_b = 0, before_e = 0;
+        for (int w = 0; w < (tid >> 5); ++w) { before_b += sh.warp[w] & 0xffffu; before_e += sh.warp[w] >> 16; }
+        const unsigned lane_lt = (1u << (tid & 31)) - 1u;
+        const unsigned eq_rank = sh.base_eq[c] + before_e + __popc(bal_e & lane_lt);
+        if (below || (eq && eq_rank < n_eq[c])) {
+          const unsigned pos = sh.base_below[c] + before_b + __popc(bal_b & lane_lt) + min(eq_rank, n_eq[c]);
+          if ((int)pos < cap[c]) { out_idx[c][pos] = e; out_valid[c][pos] = 1; }
+        }
+        __syncthreads();
+        if (tid == 0) {
+          unsigned tb = 0, te = 0;
+          for (int w = 0; w < kSampThreads / 32; ++w) { tb += sh.warp[w] & 0xffffu; te += sh.warp[w] >> 16; }
+          sh.base_below[c] += tb;
+          sh.base_eq[c] += te;
+        }
+        __syncthreads();
+      }
+    }
+  }
+  for (int c = 0; c < 2; ++c)
+    for (int i = (int)k[c] + tid; i < cap[c]; i += kSampThreads) { out_idx[c][i] = 0; out_valid[c][i] = 0; }
+  if (tid == 0) { counts[2 * img] = (int)k[1]; counts[2 * img + 1] = (int)k[0]; }
 }
 
 }  // namespace dgod
