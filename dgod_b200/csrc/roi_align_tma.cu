@@ -391,10 +391,21 @@ msroi_fwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, int n_ro
         }
         const float4 a03 = lds_f4(ay_s + (unsigned)i * 32u), a46 = lds_f4(ay_s + (unsigned)i * 32u + 16u);
         const float ay[kP] = {a03.x, a03.y, a03.z, a03.w, a46.x, a46.y, a46.z};
+#ifndef DGOD_FWD_DENSE_AY
+        // a feature row carries weight for 1-2 of the 7 bin rows (all 7 only for RoIs under a few pixels): skip the others
+#pragma unroll
+        for (int ph = 0; ph < kP; ++ph) {
+          if (ay[ph] != 0.f) {                                // warp-uniform (broadcast table read)
+#pragma unroll
+            for (int pw = 0; pw < kP; ++pw) acc[ph * kP + pw] = __ffma2_rn(make_float2(ay[ph], ay[ph]), rx[pw], acc[ph * kP + pw]);
+          }
+        }
+#else
 #pragma unroll
         for (int ph = 0; ph < kP; ++ph)
 #pragma unroll
           for (int pw = 0; pw < kP; ++pw) acc[ph * kP + pw] = __ffma2_rn(make_float2(ay[ph], ay[ph]), rx[pw], acc[ph * kP + pw]);
+#endif
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&f.empty[st]);       // this warp is done with stage st
         if (++st == n_stage) { st = 0; phase ^= 1u; }

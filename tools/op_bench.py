@@ -265,9 +265,88 @@ def bench_grl(args, out):
         out.append(row("grl_scale", "x".join(map(str, shape)), us, 2 * x.numel() * 4))
 
 
+def bench_sampler(args, out):
+    """BalancedPositiveNegativeSampler (TV _utils.py:11-71): the one-launch kernel vs the two-topk torch formulation."""
+    for (n, P, S, dt, tag) in [(155520, 128, 256, torch.float32, "RPN anchors 608x1024"), (268569, 128, 256, torch.float32, "RPN anchors 800x1344"),
+                               (2020, 128, 512, torch.int64, "RoI heads 2000 proposals + 20 GT")]:
+        g = synth.gen(n)
+        r = torch.rand(8, n, generator=g)
+        lab = torch.full((8, n), -1.0)
+        lab[r < 0.6] = 0.0
+        lab[r < 0.002] = 1.0
+        labels, keys = lab.to(dt).to(DEV), torch.rand(8, n, generator=g).to(DEV)
+        us = time_op(lambda: ops.balanced_sample(labels, keys, P, S), args.iters)
+        out.append(row("balanced_sample", f"B8 x {n} ({tag})", us, 8 * n * (labels.element_size() + 4) + 8 * (P + S) * 9))
+        if args.tv:
+            def two_topk():
+                pk = torch.where(labels >= 1, keys, torch.full_like(keys, 2.0))
+                nk = torch.where(labels == 0, keys, torch.full_like(keys, 2.0))
+                return torch.topk(pk, min(P, n), dim=1, largest=False), torch.topk(nk, min(S, n), dim=1, largest=False)
+            us = time_op(two_topk, args.iters)
+            out.append(row("torch_two_topk_sampler", f"B8 x {n} ({tag})", us, 8 * n * (labels.element_size() + 4)))
+
+
+def bench_fcos_post(args, out):
+    """FCOS eval candidates (fcos.py:576-597): one launch vs the per-image, per-level ATen chain of the reference."""
+    from dgod_b200.detector import grid_anchors
+    for (h, w) in [(608, 1024), (800, 1344)]:
+        strides = (8, 16, 32, 64, 128)
+        grids = [(-(-h // s), -(-w // s)) for s in strides]
+        cells = [torch.tensor([[-4.0 * s, -4.0 * s, 4.0 * s, 4.0 * s]]) for s in strides]
+        npl = [gh * gw for gh, gw in grids]
+        a = grid_anchors(cells, grids, [(s, s) for s in strides], DEV).float()
+        n = a.shape[0]
+        g = synth.gen(5)
+        cl = (torch.randn(8, n, 9, generator=g) * 2.5 - 2.0).to(DEV)
+        rg = (torch.rand(8, n, 4, generator=g) * 3 + 0.1).to(DEV)
+        ct = (torch.randn(8, n, 1, generator=g) * 1.5).to(DEV)
+        sizes = torch.tensor([[float(h), float(w)]] * 8, device=DEV)
+        us = time_op(lambda: ops.fcos_candidates(cl, rg, ct, a, npl, sizes, 0.2, 1000), args.iters)
+        out.append(row("fcos_candidates", f"B8 {n} locations x 9 classes, top-1000 x 5 levels", us, 8 * n * 40 + 8 * 5000 * 45))
+        if args.tv:
+            def chain():
+                res = []
+                for i in range(8):
+                    off = 0
+                    for nl in npl:
+                        s_ = torch.sqrt(torch.sigmoid(cl[i, off:off + nl]) * torch.sigmoid(ct[i, off:off + nl])).flatten()
+                        keep = s_ > 0.2
+                        s2 = s_[keep]
+                        idx = torch.where(keep)[0]
+                        k = min(1000, idx.numel())
+                        s2, j = s2.topk(k)
+                        idx = idx[j]
+                        ai = torch.div(idx, 9, rounding_mode="floor")
+                        an, r = a[off + ai], rg[i, off + ai]
+                        cx, cy = 0.5 * (an[:, 0] + an[:, 2]), 0.5 * (an[:, 1] + an[:, 3])
+                        wv, hv = an[:, 2] - an[:, 0], an[:, 3] - an[:, 1]
+                        bx = torch.stack((cx - r[:, 0] * wv, cy - r[:, 1] * hv, cx + r[:, 2] * wv, cy + r[:, 3] * hv), 1)
+                        res.append((ops.clip_boxes_to_image(bx, (h, w)), s2, idx % 9))
+                        off += nl
+                return res
+            us = time_op(chain, args.iters)
+            out.append(row("torch_fcos_candidates (ATen chain of fcos.py:576-597)", f"B8 {n} locations", us, 8 * n * 40 + 8 * 5000 * 45))
+
+
+def bench_grl_conv(args, out):
+    """GRL in front of ImageDAFPN.Conv1 (DGcommon.py:73-74): stand-alone kernel + conv vs the reversal folded into the dgrad."""
+    conv = torch.nn.Conv2d(256, 256, 3, stride=(2, 4)).to(DEV).to(memory_format=torch.channels_last)
+    x = torch.randn(8, 256, 152, 256, device=DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    for name, fn in (("grl_conv2d fwd+bwd (fused into dgrad)", lambda: ops.grl_conv2d(x, conv)),
+                     ("grad_reverse + conv fwd+bwd (separate 637 MB pass)", lambda: conv(ops.grad_reverse(x)))):
+        y = fn()
+        go = torch.randn_like(y)
+
+        def step():
+            x.grad = None
+            fn().backward(go)
+        us = time_op(step, args.iters)
+        out.append(row(name, "8x256x152x256 -> Conv2d(256,256,3,stride=(2,4))", us, 2 * x.numel() * 4))
+
+
 def main():
     p = argparse.ArgumentParser()
-    p.add_argument("--ops", default="roi,nms,match,fcos,rpn,grl,transform")
+    p.add_argument("--ops", default="roi,nms,match,fcos,rpn,grl,transform,sampler,fcos_post,grl_conv")
     p.add_argument("--iters", type=int, default=20)
     p.add_argument("--batch", type=int, default=8)
     p.add_argument("--height", type=int, default=608)
@@ -279,7 +358,7 @@ def main():
     args = p.parse_args()
     out = []
     table = {"roi": bench_roi, "nms": bench_nms, "match": bench_match, "fcos": bench_fcos, "rpn": bench_rpn, "grl": bench_grl,
-             "transform": bench_transform}
+             "transform": bench_transform, "sampler": bench_sampler, "fcos_post": bench_fcos_post, "grl_conv": bench_grl_conv}
     for name in args.ops.split(","):
         table[name](args, out)
     if args.json:
