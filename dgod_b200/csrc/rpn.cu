@@ -128,7 +128,7 @@ __device__ void radix_select(KeyFn keyfn, int m0, int m1, int k, SelShared* sh, 
   T = prefix; n_lt = lt_total; n_eq = eq;
 }
 
-// s_sel / s_count may be distributed-shared-memory pointers into the cluster's rank-0 CTA
+// warp-aggregated append to a list in the CTA's own shared memory
 __device__ __forceinline__ void append_selected(bool sel, unsigned long long rec,
                                                 unsigned long long* s_sel, int* s_count) {
   const uint32_t bal = __ballot_sync(0xffffffffu, sel);
@@ -145,14 +145,21 @@ __device__ __forceinline__ float sigmoid_rn(float x) {
   return (float)(1.0 / (1.0 + exp(-(double)x)));
 }
 
-// One CTA per (level, image): top-k of the level's objectness, sorted, decoded, filtered.
+// One 8-CTA cluster per (level, image): top-k of the level's objectness, sorted, decoded, filtered.
+//   * every CTA owns a contiguous slice of the level and keeps its keys (~ordered logit) in shared memory after the
+//     first pass, so the 4-5 passes of the radix select and the selection pass read DRAM / L2 once;
+//   * the survivors stay in the CTA that found them: it sorts its own list (bitonic, shared memory), and after one
+//     cluster barrier ranks every record against the seven other sorted lists by binary search through distributed
+//     shared memory — the rank is the candidate's position in the level's descending-score order;
+//   * every CTA decodes, clips and filters its own survivors.
 __global__ void __cluster_dims__(kTopkCluster, 1, 1) __launch_bounds__(kTopkThreads)
 rpn_topk_decode_kernel(const RpnDev g, const float* __restrict__ proposals_flat,
                        const float* __restrict__ objectness_flat,
-                       const float* __restrict__ image_sizes, float4* __restrict__ sbox,
+                       const float* __restrict__ image_sizes, int kp_max, int cache_keys, float4* __restrict__ sbox,
                        float* __restrict__ cscore, uint8_t* __restrict__ alive,
                        uint32_t* __restrict__ runkey) {
-  extern __shared__ unsigned long long s_sel[];  // next_pow2(k) records: ~ordered(logit):32 | r:32 (rank 0's is used)
+  extern __shared__ unsigned long long s_sel[];  // kp_max records: ~ordered(logit):32 | r:32, then the key cache
+  uint32_t* s_keys = reinterpret_cast<uint32_t*>(s_sel + kp_max);
   __shared__ SelShared s_sh;
   __shared__ int s_count;
   cg::cluster_group cluster = cg::this_cluster();
@@ -168,26 +175,38 @@ rpn_topk_decode_kernel(const RpnDev g, const float* __restrict__ proposals_flat,
     const int a = m / HW, rem = m - a * HW;
     return (uint32_t)(rem * A + a);
   };
-  auto key_logit = [&](int m, uint32_t& key) -> bool {
-    key = ~float_ordered(__ldg(obj + m) + 0.f);  // smallest key = largest logit
-    return true;
-  };
-  int kp = 1;
-  while (kp < k) kp <<= 1;
   if (threadIdx.x == 0) s_count = 0;
   // this CTA's slice of the level
   const int slice = (n + kTopkCluster - 1) / kTopkCluster;
   const int m0 = min((int)rank * slice, n), m1 = min(m0 + slice, n);
-  unsigned long long* sel0 = cluster.map_shared_rank(s_sel, 0);
-  int* count0 = cluster.map_shared_rank(&s_count, 0);
-  cluster.sync();
+  const bool cached = slice <= cache_keys;
+  if (cached) {
+    for (int base = m0; base < m1; base += kSelUnroll * blockDim.x) {
+      float v[kSelUnroll];
+#pragma unroll
+      for (int u = 0; u < kSelUnroll; ++u) {
+        const int m = base + u * blockDim.x + threadIdx.x;
+        v[u] = m < m1 ? __ldg(obj + m) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kSelUnroll; ++u) {
+        const int m = base + u * blockDim.x + threadIdx.x;
+        if (m < m1) s_keys[m - m0] = ~float_ordered(v[u] + 0.f);
+      }
+    }
+  }
+  auto key_logit = [&](int m, uint32_t& key) -> bool {
+    key = cached ? s_keys[m - m0] : ~float_ordered(__ldg(obj + m) + 0.f);  // smallest key = largest logit
+    return true;
+  };
+  __syncthreads();
 
   if (n <= k) {
     for (int base = m0; base < m1; base += blockDim.x) {
       const int m = base + threadIdx.x;
       uint32_t key = 0u;
       const bool sel = m < m1 && key_logit(m, key);
-      append_selected(sel, ((unsigned long long)key << 32) | ref_index(m < m1 ? m : 0), sel0, count0);
+      append_selected(sel, ((unsigned long long)key << 32) | ref_index(m < m1 ? m : 0), s_sel, &s_count);
     }
   } else {
     uint32_t T; int n_lt, n_eq;
@@ -221,18 +240,20 @@ rpn_topk_decode_kernel(const RpnDev g, const float* __restrict__ proposals_flat,
           r = ref_index(m);
           sel = keys[u] < T || (keys[u] == T && r <= T2);
         }
-        append_selected(sel, ((unsigned long long)keys[u] << 32) | r, sel0, count0);   // into rank 0 via DSMEM
+        append_selected(sel, ((unsigned long long)keys[u] << 32) | r, s_sel, &s_count);
       }
     }
   }
-  cluster.sync();          // every CTA's survivors are in rank 0's list
-  if (rank != 0) return;   // rank 0 sorts, decodes and filters the k survivors
-  for (int i = k + threadIdx.x; i < kp; i += blockDim.x) s_sel[i] = ~0ull;
   __syncthreads();
-  // bitonic sort of the kp records, ascending: logit descending, ties by reference index
-  for (int kk = 2; kk <= kp; kk <<= 1) {
+  // own survivors, ascending: logit descending, ties by reference index
+  const int mine = s_count;
+  int tile = 2;
+  while (tile < mine) tile <<= 1;
+  for (int i = mine + threadIdx.x; i < tile; i += blockDim.x) s_sel[i] = ~0ull;
+  __syncthreads();
+  for (int kk = 2; kk <= tile; kk <<= 1) {
     for (int j = kk >> 1; j > 0; j >>= 1) {
-      for (int q = threadIdx.x; q < (kp >> 1); q += blockDim.x) {
+      for (int q = threadIdx.x; q < (tile >> 1); q += blockDim.x) {
         const int i = 2 * q - (q & (j - 1)), o = i + j;
         const bool asc = (i & kk) == 0;
         const unsigned long long x = s_sel[i], y = s_sel[o];
@@ -241,10 +262,37 @@ rpn_topk_decode_kernel(const RpnDev g, const float* __restrict__ proposals_flat,
       __syncthreads();
     }
   }
+  cluster.sync();          // every CTA's list is sorted and its count final
 
+  const unsigned long long* lists[kTopkCluster];
+  int counts[kTopkCluster];
+#pragma unroll
+  for (int r = 0; r < kTopkCluster; ++r) {
+    lists[r] = cluster.map_shared_rank(s_sel, r);
+    counts[r] = *cluster.map_shared_rank(&s_count, r);
+  }
   const float img_h = image_sizes[2 * b], img_w = image_sizes[2 * b + 1];
-  for (int j = threadIdx.x; j < k; j += blockDim.x) {
-    const unsigned long long rec = s_sel[j];
+  for (int t = threadIdx.x; t < mine; t += blockDim.x) {
+    const unsigned long long rec = s_sel[t];
+    // records are unique (the reference index is): position = #records of the level that sort before this one
+    int lo[kTopkCluster], len[kTopkCluster];
+#pragma unroll
+    for (int r = 0; r < kTopkCluster; ++r) { lo[r] = 0; len[r] = (r == (int)rank) ? 0 : counts[r]; }
+    for (int it = kp_max; it > 0; it >>= 1) {        // log2(kp_max) + 1 halvings, the eight searches in lockstep
+#pragma unroll
+      for (int r = 0; r < kTopkCluster; ++r) {
+        if (len[r] > 0) {
+          const int half = len[r] >> 1;
+          const bool less = lists[r][lo[r] + half] < rec;
+          lo[r] = less ? lo[r] + half + 1 : lo[r];
+          len[r] = less ? len[r] - half - 1 : half;
+        }
+      }
+    }
+    int j = t;
+#pragma unroll
+    for (int r = 0; r < kTopkCluster; ++r) j += lo[r];
+
     const uint32_t r = (uint32_t)rec;
     const float logit = float_from_ordered(~(uint32_t)(rec >> 32));
     float x1, y1, x2, y2;
@@ -283,6 +331,7 @@ rpn_topk_decode_kernel(const RpnDev g, const float* __restrict__ proposals_flat,
     alive[pos] = ok ? 1 : 0;
     runkey[pos] = (uint32_t)(b * DGOD_MAX_LEVELS + l);
   }
+  cluster.sync();          // no CTA leaves while its list may still be read
 }
 
 // Merge the per-level kept lists of an image by descending score (ties: lower level, then
@@ -294,10 +343,16 @@ rpn_merge_kernel(const RpnDev g, int post_nms_top_n, const float4* __restrict__ 
                  float* __restrict__ out_scores, int32_t* __restrict__ out_count) {
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t == 0) {
+  {
     int tot = 0;
     for (int l = 0; l < g.n_levels; ++l) tot += run_count[b * DGOD_MAX_LEVELS + l];
-    out_count[b] = min(tot, post_nms_top_n);
+    tot = min(tot, post_nms_top_n);
+    if (t == 0) out_count[b] = tot;
+    // rows behind the image's last proposal are zero (the outputs are fixed-capacity)
+    for (int r = tot + t; r < post_nms_top_n; r += gridDim.x * blockDim.x) {
+      reinterpret_cast<float4*>(out_boxes)[(size_t)b * post_nms_top_n + r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      out_scores[(size_t)b * post_nms_top_n + r] = 0.f;
+    }
   }
   if (t >= g.k_tot) return;
   int l = 0;
@@ -369,7 +424,7 @@ static size_t carve_rpn(Workspace& ws, RpnBuffers& b, const RpnDev& g) {
   b.run_count = ws.take<int32_t>((size_t)(g.n_img > 0 ? g.n_img : 1) * DGOD_MAX_LEVELS);
   b.keepbits = ws.take<unsigned long long>(n_pos / 64 + 1);
   b.diag_cols = ws.take<unsigned long long>(n_pos);
-  b.mask = ws.take<unsigned long long>(n_pos * nms_mask_row_words(max_k));
+  b.mask = ws.take<unsigned long long>(nms_mask_rows(n_pos) * nms_mask_row_words(max_k));
   return ws.used;
 }
 
@@ -389,27 +444,28 @@ static int rpn_run(const dgod_rpn_config* cfg, RpnDev& g, const float* proposals
   const int n_pos = g.n_img * g.k_tot;
   int max_k = 1;
   for (int l = 0; l < g.n_levels; ++l) max_k = g.k_l[l] > max_k ? g.k_l[l] : max_k;
-  int kp = 1;
+  int kp = 2;
   while (kp < max_k) kp <<= 1;
-  const size_t smem = (size_t)kp * sizeof(unsigned long long);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DGOD_CUDA(cudaFuncSetAttribute(rpn_topk_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   8192 * (int)sizeof(unsigned long long)));
-    attr_set = true;
+  // shared memory: the CTA's survivor list (all k may come from one slice) + the key cache of its slice
+  int max_slice = 1;
+  for (int l = 0; l < g.n_levels; ++l) max_slice = max(max_slice, (g.n_l[l] + kTopkCluster - 1) / kTopkCluster);
+  const size_t list_bytes = (size_t)kp * sizeof(unsigned long long);
+  const size_t cache_cap = (size_t)(200 * 1024) - list_bytes;
+  const int cache_keys = (size_t)max_slice * 4 <= cache_cap ? max_slice : 0;     // too large an image: re-read the logits
+  const size_t smem = list_bytes + (size_t)cache_keys * sizeof(uint32_t);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    DGOD_CUDA(cudaFuncSetAttribute(rpn_topk_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
   }
-  const size_t post = (size_t)cfg->post_nms_top_n;
-  DGOD_CUDA(cudaMemsetAsync(out_boxes, 0, (size_t)g.n_img * post * 4 * sizeof(float), st));
-  DGOD_CUDA(cudaMemsetAsync(out_scores, 0, (size_t)g.n_img * post * sizeof(float), st));
-  DGOD_CUDA(cudaMemsetAsync(b.keepbits, 0, ((size_t)n_pos / 64 + 1) * sizeof(unsigned long long), st));
-  DGOD_CUDA(cudaMemsetAsync(b.run_count, 0, (size_t)g.n_img * DGOD_MAX_LEVELS * sizeof(int32_t), st));
-
+  // no memset: every (image, level) is a run (k_l >= 1), so the scan writes every run_count the merge reads, and the
+  // merge zero-fills the output rows behind each image's count
   rpn_topk_decode_kernel<<<dim3(g.n_levels * kTopkCluster, g.n_img), kTopkThreads, smem, st>>>(
-      g, proposals_flat, objectness_flat, image_sizes, b.sbox, b.cscore, b.alive, b.runkey);
+      g, proposals_flat, objectness_flat, image_sizes, kp, cache_keys, b.sbox, b.cscore, b.alive, b.runkey);
   DGOD_LAUNCHED();
   int rc = launch_nms_mask(b.sbox, b.runkey, n_pos, max_k, float_round_down(cfg->nms_thresh), b.mask, b.diag_cols, st);
   if (rc) return rc;
-  rc = launch_nms_scan(b.mask, b.diag_cols, b.runkey, b.alive, n_pos, max_k, b.keepbits, b.compact, b.run_count, st);
+  rc = launch_nms_scan(b.mask, b.diag_cols, b.runkey, b.alive, n_pos, max_k, nullptr, b.compact, b.run_count, st);
   if (rc) return rc;
   rpn_merge_kernel<<<dim3(cdiv(g.k_tot, 256), g.n_img), 256, 0, st>>>(
       g, cfg->post_nms_top_n, b.sbox, b.cscore, b.compact, b.run_count, out_boxes, out_scores, out_count);
