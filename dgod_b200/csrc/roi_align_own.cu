@@ -147,9 +147,11 @@ __device__ __forceinline__ float axis_weight(const short* lo, const short* hi, c
 constexpr int kPlanWarps = 4;
 
 __global__ void __launch_bounds__(kPlanWarps * 32)
-own_plan_kernel(const RoiDev g, const float* __restrict__ rois, int n_rois, Plan* __restrict__ plans, Bin* __restrict__ bins) {
+own_plan_kernel(const RoiDev g, const float* __restrict__ rois, int n_rois, Plan* __restrict__ plans, Bin* __restrict__ bins,
+                int* __restrict__ cursor) {
   __shared__ Scratch scratch[kPlanWarps];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *cursor = 0;      // the bin kernel (next in the stream) counts pairs from zero
   const int k = blockIdx.x * kPlanWarps + w;
   if (k >= n_rois) return;
   Scratch& t = scratch[w];
@@ -296,8 +298,19 @@ own_bin_kernel(const Tiles tg, const Bin* __restrict__ bins, int n_rois, const i
   const TileAt a = tile_at(tg, t);
   int k_begin = 0, k_end = n_rois;
   if (roi_img_offsets) { k_begin = roi_img_offsets[a.b]; k_end = roi_img_offsets[a.b + 1]; }
+  // pass 1: count the hits, remembering those of the first 1024 RoIs of the image as one bit per chunk of 32 (the loads of
+  // consecutive chunks are independent: unrolled, they are in flight together instead of one L2 round trip per chunk)
   int cnt = 0;
-  for (int base = k_begin; base < k_end; base += 32) cnt += __popc(__ballot_sync(0xffffffffu, bin_hit(bins, base + lane, k_end, a)));
+  unsigned bits = 0;
+  {
+    int c = 0;
+#pragma unroll 8
+    for (int base = k_begin; base < k_end; base += 32, ++c) {
+      const bool hit = bin_hit(bins, base + lane, k_end, a);
+      if (c < 32 && hit) bits |= 1u << c;
+      cnt += __popc(__ballot_sync(0xffffffffu, hit));
+    }
+  }
   int off = 0;
   if (lane == 0) {
     off = cnt ? atomicAdd(cursor, cnt) : 0;
@@ -305,11 +318,15 @@ own_bin_kernel(const Tiles tg, const Bin* __restrict__ bins, int n_rois, const i
   }
   if (!cnt) return;
   off = __shfl_sync(0xffffffffu, off, 0);
-  for (int base = k_begin; base < k_end; base += 32) {
-    const bool hit = bin_hit(bins, base + lane, k_end, a);
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (hit) pair_k[off + __popc(m & ((1u << lane) - 1u))] = base + lane;
-    off += __popc(m);
+  {
+    int c = 0;
+#pragma unroll 4
+    for (int base = k_begin; base < k_end; base += 32, ++c) {
+      const bool hit = c < 32 ? ((bits >> c) & 1u) : bin_hit(bins, base + lane, k_end, a);
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) pair_k[off + __popc(m & ((1u << lane) - 1u))] = base + lane;
+      off += __popc(m);
+    }
   }
 }
 
@@ -769,10 +786,11 @@ static int launch_own(const RoiDev& g, const own::Tiles& tg, const OwnLayout& L,
   int2* tile_list = reinterpret_cast<int2*>(ws + L.tile_list);
   int* pair_k = reinterpret_cast<int*>(ws + L.pair_k);
   own::Plan* plans = reinterpret_cast<own::Plan*>(ws + L.plans);
-  DGOD_CUDA(cudaMemsetAsync(cursor, 0, own::kCounterBytes, st));
   if (n_rois > 0) {
-    own::own_plan_kernel<<<cdiv(n_rois, own::kPlanWarps), own::kPlanWarps * 32, 0, st>>>(g, rois, n_rois, plans, bins);
+    own::own_plan_kernel<<<cdiv(n_rois, own::kPlanWarps), own::kPlanWarps * 32, 0, st>>>(g, rois, n_rois, plans, bins, cursor);
     DGOD_LAUNCHED();
+  } else {
+    DGOD_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int), st));
   }
   own::own_bin_kernel<<<cdiv(tg.n_tiles, own::kBinWarps), own::kBinWarps * 32, 0, st>>>(tg, bins, n_rois, roi_img_offsets, tile_list,
                                                                                       pair_k, cursor);
