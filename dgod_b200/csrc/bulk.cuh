@@ -46,6 +46,55 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 #endif
 }
+// The same on 32-bit shared-window addresses computed once (smem_opaque): with generic pointers to static shared
+// variables the compiler rematerialises the window base (S2R SR_CgaCtaId + LEA) in front of every barrier operation.
+__device__ __forceinline__ unsigned smem_opaque(const void* p) {
+  unsigned a;
+  asm volatile("mov.u32 %0, %1;\n" : "=r"(a) : "r"(smem_u32(p)));
+  return a;
+}
+__device__ __forceinline__ void mbar_wait_s(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAITS_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONES_%=;\n"
+      "bra WAITS_%=;\n"
+      "DONES_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_s(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_s(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(unsigned a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4s(unsigned a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds_f32s(unsigned a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds_bf16s(unsigned a) {       // bf16 -> fp32 (exact)
+  unsigned short u;
+  asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(u) : "r"(a));
+  return __uint_as_float((unsigned)u << 16);
+}
+__device__ __forceinline__ unsigned lds_u8s(unsigned a) {
+  unsigned v;
+  asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(v) : "r"(a));
+  return v;
+}
 // Pure polling (test_wait never suspends the thread): for waits on the critical path of a producer/consumer ring.
 __device__ __forceinline__ void mbar_spin(unsigned long long* bar, unsigned parity) {
   asm volatile(

@@ -350,6 +350,10 @@ template <> __device__ __forceinline__ float lds_as_f32<__nv_bfloat16>(const __n
   return __uint_as_float((unsigned)(*reinterpret_cast<const unsigned short*>(p)) << 16);
 }
 
+template <typename T> __device__ __forceinline__ float lds_g(unsigned a);        // gradient element at a 32-bit shared address
+template <> __device__ __forceinline__ float lds_g<float>(unsigned a) { return lds_f32s(a); }
+template <> __device__ __forceinline__ float lds_g<__nv_bfloat16>(unsigned a) { return lds_bf16s(a); }
+
 // acc[r] += sum_pw w[pw] * t[r][pw]: all 7 bins (the general form)
 __device__ __forceinline__ void column_dense(const float4 w0, const float4 w1, const float2 (&t)[kRPW][kP], float2 (&acc)[kRPW][kTileW],
                                              int x) {
@@ -363,10 +367,10 @@ __device__ __forceinline__ void column_dense(const float4 w0, const float4 w1, c
 // One block of 4 tile columns whose weights sit on bins P0 .. P0+3 (the plan's wblk row): 4 broadcast reads, then
 // 4 columns x kRPW rows x 4 multiply-adds with no branch and no dependence between columns.
 template <int B, int P0>
-__device__ __forceinline__ void column_block(const float4* __restrict__ wtab, const float2 (&t)[kRPW][kP], float2 (&acc)[kRPW][kTileW]) {
+__device__ __forceinline__ void column_block(unsigned wtab, const float2 (&t)[kRPW][kP], float2 (&acc)[kRPW][kTileW]) {
   float4 w[kBlk];
 #pragma unroll
-  for (int c = 0; c < kBlk; ++c) w[c] = wtab[c];
+  for (int c = 0; c < kBlk; ++c) w[c] = lds_f4s(wtab + 16u * c);
 #pragma unroll
   for (int c = 0; c < kBlk; ++c)
 #pragma unroll
@@ -387,14 +391,14 @@ __device__ __forceinline__ void column_block(const float4* __restrict__ wtab, co
 
 // `blocks`: byte B describes the tile's block B (bits 0-1: base bin, bit 2: has weight); `w`: its 4 table entries
 template <int B>
-__device__ __forceinline__ void column_block_any(unsigned blocks, const float4* __restrict__ w, const float2 (&t)[kRPW][kP],
+__device__ __forceinline__ void column_block_any(unsigned blocks, unsigned w, const float2 (&t)[kRPW][kP],
                                                  float2 (&acc)[kRPW][kTileW]) {
   if ((blocks >> (8 * B + 2)) & 1u) {
     const unsigned p0 = (blocks >> (8 * B)) & 3u;
-    if (p0 == 0) column_block<B, 0>(w + B * kBlk, t, acc);
-    else if (p0 == 1) column_block<B, 1>(w + B * kBlk, t, acc);
-    else if (p0 == 2) column_block<B, 2>(w + B * kBlk, t, acc);
-    else column_block<B, 3>(w + B * kBlk, t, acc);
+    if (p0 == 0) column_block<B, 0>(w + 16u * (B * kBlk), t, acc);
+    else if (p0 == 1) column_block<B, 1>(w + 16u * (B * kBlk), t, acc);
+    else if (p0 == 2) column_block<B, 2>(w + 16u * (B * kBlk), t, acc);
+    else column_block<B, 3>(w + 16u * (B * kBlk), t, acc);
   }
 }
 
@@ -405,8 +409,12 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
   constexpr int NS = Cfg<T>::kStages;
   constexpr int SB = Cfg<T>::kStageBytes;
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ alignas(8) unsigned long long full[NS], ready[NS], empty[NS];
-  __shared__ PairInfo info[NS];
+  struct alignas(16) RingSync { PairInfo info[NS]; unsigned long long full[NS], ready[NS], empty[NS]; };
+  __shared__ RingSync rs;
+  PairInfo* const info = rs.info;
+  unsigned long long* const full = rs.full;
+  unsigned long long* const ready = rs.ready;
+  unsigned long long* const empty = rs.empty;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_items = tg.n_tiles * tg.n_slices;
 
@@ -424,6 +432,10 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
     tmap_prefetch(&tm_g);
   }
   __syncthreads();
+  // 32-bit shared-window addresses of the ring's bookkeeping, computed once and opaque to the compiler
+  const unsigned rs_s = smem_opaque(&rs), smem_s = smem_opaque(smem);
+  constexpr unsigned kFullOff = (unsigned)offsetof(RingSync, full), kReadyOff = (unsigned)offsetof(RingSync, ready),
+                     kEmptyOff = (unsigned)offsetof(RingSync, empty);
 
   if (warp == kWarps) {
     // ------------------------------------------------------------------ producer.  Walks the pair lists of this CTA's
@@ -461,8 +473,8 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
           const int k = __shfl_sync(0xffffffffu, kk, i);
           if (lane == 0) {
             unsigned char* st = smem + (size_t)s * SB;
-            if (q >= (unsigned)NS) OWN_WAIT(&empty[s], phase ^ 1u);
-            mbar_expect_tx(&full[s], (unsigned)SB);
+            if (q >= (unsigned)NS) mbar_wait_s(rs_s + kEmptyOff + s * 8u, phase ^ 1u);
+            mbar_expect_tx_s(rs_s + kFullOff + s * 8u, (unsigned)SB);
             tmap_load_2d(st, &tm_plan, 0, k * Cfg<T>::kPlanBoxRows, &full[s]);
             tmap_load_2d(st + sizeof(Plan), &tm_g, 0, k * rows_per_roi + sl * Cfg<T>::kGBoxRows, &full[s]);
           }
@@ -485,7 +497,7 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
       const int2 lc = lc_next;
       if (it + (int)gridDim.x < n_items) lc_next = __ldg(tile_list + (it + gridDim.x) / tg.n_slices);   // next item's list, early
       for (int p = 0; p < lc.y; ++p) {
-        OWN_WAIT(&full[s], phase);
+        mbar_wait_s(rs_s + kFullOff + s * 8u, phase);
         const Plan& P = *reinterpret_cast<const Plan*>(smem + (size_t)s * SB);
         const int rel_r = lane < kMaxLive ? (int)P.rows[lane] - a.y0 : 0x7fff;      // padding entries are 0x7fff
         const unsigned rowmask = __reduce_or_sync(0xffffffffu, (rel_r >= 0 && rel_r < kTileH) ? (1u << rel_r) : 0u);
@@ -544,7 +556,7 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
           I.rowmask = colmask ? rowmask : 0u;          // no live column in this tile: nothing to do for any warp
           I.i_first = i_first; I.blocks = blocks; I.w_off = w_off;
           I.colmask = colmask; I.j_first = j_first;
-          mbar_arrive(&ready[s]);                      // release: the stores above are visible to whoever observes the phase
+          mbar_arrive_s(rs_s + kReadyOff + s * 8u);    // release: the stores above are visible to whoever observes the phase
         }
         __syncwarp();
         if (++s == (unsigned)NS) { s = 0; phase ^= 1u; }
@@ -577,16 +589,15 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
 #ifdef DGOD_OWN_TIMING
       const long long tw = clock64();
 #endif
-      OWN_WAIT(&ready[s], phase);
+      mbar_wait_s(rs_s + kReadyOff + s * 8u, phase);
 #ifdef DGOD_OWN_TIMING
       t_wait += clock64() - tw;
 #endif
-      const uint4 ia = *reinterpret_cast<const uint4*>(&info[s]);               // rowmask, i_first, blocks, w_off
+      const uint4 ia = lds_u4(rs_s + s * (unsigned)sizeof(PairInfo));             // rowmask, i_first, blocks, w_off
       const unsigned rm = (ia.x >> r0) & ((1u << kRPW) - 1u);
       {
         if (rm) {
-        const unsigned char* st = smem + (size_t)s * SB;
-        const Plan& P = *reinterpret_cast<const Plan*>(st);
+        const unsigned st_s = smem_s + s * (unsigned)SB;                       // this stage: plan, then the gradient slice
         int idx[kRPW];
         {
           const int i0 = (int)ia.y + __popc(ia.x & ((1u << r0) - 1u));          // list index of this warp's first live row
@@ -599,26 +610,26 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
         for (int r = 0; r < kRPW; ++r) {
           const bool live = (rm >> r) & 1u;
           const float z = live ? 1.f : 0.f;                                     // a dead row reads row 0 of the table, times zero
-          const float4* pa = reinterpret_cast<const float4*>(P.ay[idx[r]]);
-          const float4 u0 = pa[0], u1 = pa[1];
+          const unsigned pa = st_s + (unsigned)offsetof(Plan, ay) + (unsigned)idx[r] * 32u;
+          const float4 u0 = lds_f4s(pa), u1 = lds_f4s(pa + 16u);
           ay[r][0] = u0.x * z; ay[r][1] = u0.y * z; ay[r][2] = u0.z * z; ay[r][3] = u0.w * z;
           ay[r][4] = u1.x * z; ay[r][5] = u1.y * z; ay[r][6] = u1.z * z;
-          phm |= live ? (unsigned)P.aymask[idx[r]] : 0u;
+          phm |= live ? lds_u8s(st_s + (unsigned)offsetof(Plan, aymask) + (unsigned)idx[r]) : 0u;
         }
         float2 t[kRPW][kP];
 #pragma unroll
         for (int r = 0; r < kRPW; ++r)
 #pragma unroll
           for (int pw = 0; pw < kP; ++pw) t[r][pw] = make_float2(0.f, 0.f);
-        const T* __restrict__ ga = reinterpret_cast<const T*>(st + sizeof(Plan)) + lane * kNB;
-        const T* __restrict__ gb = ga + 32 * kNB;
+        const unsigned ga = st_s + (unsigned)sizeof(Plan) + (unsigned)(lane * kNB) * (unsigned)sizeof(T);
+        const unsigned gb = ga + 32u * kNB * (unsigned)sizeof(T);
 #ifndef DGOD_OWN_SKIP_T
 #pragma unroll
         for (int ph = 0; ph < kP; ++ph) {
           if ((phm >> ph) & 1u) {                           // warp-uniform
 #pragma unroll
             for (int pw = 0; pw < kP; ++pw) {
-              const float2 gv = make_float2(lds_as_f32<T>(ga + ph * kP + pw), lds_as_f32<T>(gb + ph * kP + pw));
+              const float2 gv = make_float2(lds_g<T>(ga + (unsigned)((ph * kP + pw) * sizeof(T))), lds_g<T>(gb + (unsigned)((ph * kP + pw) * sizeof(T))));
 #pragma unroll
               for (int r = 0; r < kRPW; ++r) t[r][pw] = __ffma2_rn(make_float2(ay[r][ph], ay[r][ph]), gv, t[r][pw]);
             }
@@ -628,7 +639,7 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
 #pragma unroll
         for (int r = 0; r < kRPW; ++r)
 #pragma unroll
-          for (int pw = 0; pw < kP; ++pw) t[r][pw] = make_float2(ay[r][pw] + (float)phm, lds_as_f32<T>(ga + pw));
+          for (int pw = 0; pw < kP; ++pw) t[r][pw] = make_float2(ay[r][pw] + (float)phm, lds_g<T>(ga + (unsigned)(pw * sizeof(T))));
 #endif
 #ifdef DGOD_OWN_SKIP_COLS
 #pragma unroll
@@ -638,22 +649,23 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
 #else
         if (!(ia.z >> 31)) {
           // blocked form: the 4 absolute column blocks of this tile, branch-free inside a block
-          const float4* w = (int)ia.w == kOwnTable ? info[s].wtab : &P.wblk[0][0] + (int)ia.w;   // absent blocks are never read
+          const unsigned w = (int)ia.w == kOwnTable ? rs_s + s * (unsigned)sizeof(PairInfo) + (unsigned)offsetof(PairInfo, wtab)
+                                                    : st_s + (unsigned)offsetof(Plan, wblk) + (unsigned)((int)ia.w * 16);   // absent blocks are never read
           column_block_any<0>(ia.z, w, t, acc);
           column_block_any<1>(ia.z, w, t, acc);
           column_block_any<2>(ia.z, w, t, acc);
           column_block_any<3>(ia.z, w, t, acc);
         } else {
           // general form (columns far apart, or more than 4 bins on a block): all 7 bins per live column
-          const uint4 ib = *(reinterpret_cast<const uint4*>(&info[s]) + 1);      // colmask, j_first
+          const uint4 ib = lds_u4(rs_s + s * (unsigned)sizeof(PairInfo) + 16u);   // colmask, j_first
           const unsigned cm = ib.x;
           const int j_first = (int)ib.y;
 #pragma unroll
           for (int x = 0; x < kTileW; ++x) {
             if ((cm >> x) & 1u) {                           // warp-uniform
               const int j = j_first + __popc(cm & ((1u << x) - 1u));
-              const float4* px = reinterpret_cast<const float4*>(P.ax[j]);
-              column_dense(px[0], px[1], t, acc, x);
+              const unsigned px = st_s + (unsigned)offsetof(Plan, ax) + (unsigned)j * 32u;
+              column_dense(lds_f4s(px), lds_f4s(px + 16u), t, acc, x);
             }
           }
         }
@@ -661,7 +673,7 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
+      if (lane == 0) mbar_arrive_s(rs_s + kEmptyOff + s * 8u);
       if (++s == (unsigned)NS) { s = 0; phase ^= 1u; }
     }
 

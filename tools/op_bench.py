@@ -222,7 +222,18 @@ def bench_fcos(args, out):
             (d["classification"] + d["bbox_regression"] + d["bbox_ctrness"]).backward()
 
         us = time_op(lambda: step(True), args.iters)
-        out.append(row("fcos_loss fwd+bwd (fused)", f"B8 {n} locations", us, 3 * alg))
+        out.append(row("fcos_loss fwd+bwd (fused; through head.compute_loss, loss sum and the autograd engine)", f"B8 {n} locations", us, 3 * alg))
+        # the op calls alone (what the wrapper adds to the kernels: output allocation, one ctypes call)
+        with torch.no_grad():
+            dt = [ho["cls_logits"].detach(), ho["bbox_regression"].detach(), ho["bbox_ctrness"].detach()]
+            _, cls_t, box_t, _ = assigned
+            us = time_op(lambda: ops.fcos_loss(dt[0], dt[1], dt[2], a, cls_t, box_t), args.iters)
+            out.append(row("fcos_loss forward (op call)", f"B8 {n} locations", us, alg))
+            losses = ops.fcos_loss(dt[0], dt[1], dt[2], a, cls_t, box_t)
+            gl = torch.ones(3, device=DEV)
+            us = time_op(lambda: ops._fcos_loss_bwd_op._init_fn(dt[0], dt[1], dt[2], a.float().contiguous(), cls_t.contiguous(),
+                                                                box_t.float().contiguous(), 0.25, losses, gl), args.iters)
+            out.append(row("fcos_loss backward (op call)", f"B8 {n} locations", us, 2 * alg))
         if args.tv:
             t = time_op(lambda: step(False), args.iters)
             out.append(row("torchvision_ops_fcos_loss fwd+bwd (ATen chain of fcos.py:149-202)", f"B8 {n} locations", t, 3 * alg))
