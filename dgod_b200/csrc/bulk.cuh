@@ -95,6 +95,22 @@ __device__ __forceinline__ unsigned lds_u8s(unsigned a) {
   asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(v) : "r"(a));
   return v;
 }
+__device__ __forceinline__ int lds_s16s(unsigned a) {
+  short v;
+  asm volatile("ld.shared.s16 %0, [%1];\n" : "=h"(v) : "r"(a));
+  return (int)v;
+}
+__device__ __forceinline__ unsigned long long lds_u64s(unsigned a) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];\n" : "=l"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u4s(unsigned a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_f4s(unsigned a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 // Pure polling (test_wait never suspends the thread): for waits on the critical path of a producer/consumer ring.
 __device__ __forceinline__ void mbar_spin(unsigned long long* bar, unsigned parity) {
   asm volatile(

@@ -498,32 +498,34 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
       if (it + (int)gridDim.x < n_items) lc_next = __ldg(tile_list + (it + gridDim.x) / tg.n_slices);   // next item's list, early
       for (int p = 0; p < lc.y; ++p) {
         mbar_wait_s(rs_s + kFullOff + s * 8u, phase);
-        const Plan& P = *reinterpret_cast<const Plan*>(smem + (size_t)s * SB);
-        const int rel_r = lane < kMaxLive ? (int)P.rows[lane] - a.y0 : 0x7fff;      // padding entries are 0x7fff
+        const unsigned st_s = smem_s + s * (unsigned)SB;
+        const int rel_r = lane < kMaxLive ? lds_s16s(st_s + (unsigned)offsetof(Plan, rows) + 2u * lane) - a.y0 : 0x7fff;   // padding entries are 0x7fff
         const unsigned rowmask = __reduce_or_sync(0xffffffffu, (rel_r >= 0 && rel_r < kTileH) ? (1u << rel_r) : 0u);
         const unsigned i_first = __popc(__ballot_sync(0xffffffffu, rel_r < 0));
-        const int4 hdr = *reinterpret_cast<const int4*>(&P);
+        const uint4 hdr_u = lds_u4(st_s);
+        const int4 hdr = make_int4((int)hdr_u.x, (int)hdr_u.y, (int)hdr_u.z, (int)hdr_u.w);
         const int x_first = (short)(hdr.z & 0xffff);
         unsigned blocks = 0x80000000u, colmask = 0, j_first = 0;
         int w_off = 0;
         if (hdr.w & 0xffff) {
           const int b_first = (a.x0 >> 2) - (x_first >> 2);                       // plan block of the tile's block 0 (-3 .. 7)
-          const unsigned long long all = *reinterpret_cast<const unsigned long long*>(P.blk);
+          const unsigned long long all = lds_u64s(st_s + (unsigned)offsetof(Plan, blk));
           blocks = (b_first >= 0 ? (unsigned)(all >> (8 * b_first)) : (unsigned)(all << (8 * -b_first))) & 0x07070707u;
           w_off = b_first * kBlk;
           colmask = blocks;                                                         // only "any live column" matters below
         } else {
           // the plan has no blocked form (columns far apart, or a block of the span needs more than 4 bins): try again
           // for the 4 blocks of THIS tile from the A_x rows of its live columns; the general form is the last resort
-          const int rel_c = lane < kMaxLive ? (int)P.cols[lane] - a.x0 : 0x7fff;
+          const int rel_c = lane < kMaxLive ? lds_s16s(st_s + (unsigned)offsetof(Plan, cols) + 2u * lane) - a.x0 : 0x7fff;
           colmask = __reduce_or_sync(0xffffffffu, (rel_c >= 0 && rel_c < kTileW) ? (1u << rel_c) : 0u);
           j_first = __popc(__ballot_sync(0xffffffffu, rel_c < 0));
           float row[8];
           {
             const bool live = lane < kTileW && ((colmask >> lane) & 1u);
             const int j = (int)j_first + __popc(colmask & ((1u << lane) - 1u));
-            const float4 a0 = live ? *reinterpret_cast<const float4*>(&P.ax[j][0]) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 a1 = live ? *reinterpret_cast<const float4*>(&P.ax[j][4]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const unsigned pax = st_s + (unsigned)offsetof(Plan, ax) + (unsigned)j * 32u;
+            const float4 a0 = live ? lds_f4s(pax) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 a1 = live ? lds_f4s(pax + 16u) : make_float4(0.f, 0.f, 0.f, 0.f);
             row[0] = a0.x; row[1] = a0.y; row[2] = a0.z; row[3] = a0.w; row[4] = a1.x; row[5] = a1.y; row[6] = a1.z; row[7] = 0.f;
           }
           unsigned nz = 0;
@@ -540,7 +542,7 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
             wv.y = pb0 == 0 ? row[1] : pb0 == 1 ? row[2] : pb0 == 2 ? row[3] : row[4];
             wv.z = pb0 == 0 ? row[2] : pb0 == 1 ? row[3] : pb0 == 2 ? row[4] : row[5];
             wv.w = pb0 == 0 ? row[3] : pb0 == 1 ? row[4] : pb0 == 2 ? row[5] : row[6];
-            if (lane < kTileW) info[s].wtab[lane] = wv;
+            if (lane < kTileW) sts_f4s(rs_s + s * (unsigned)sizeof(PairInfo) + (unsigned)offsetof(PairInfo, wtab) + 16u * lane, wv);
             blocks = 0;
 #pragma unroll
             for (int b = 0; b < kTileW / kBlk; ++b) {
@@ -552,10 +554,9 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
           }
         }
         if (lane == 0) {
-          PairInfo& I = info[s];
-          I.rowmask = colmask ? rowmask : 0u;          // no live column in this tile: nothing to do for any warp
-          I.i_first = i_first; I.blocks = blocks; I.w_off = w_off;
-          I.colmask = colmask; I.j_first = j_first;
+          const unsigned is = rs_s + s * (unsigned)sizeof(PairInfo);
+          sts_u4s(is, make_uint4(colmask ? rowmask : 0u, i_first, blocks, (unsigned)w_off));   // no live column in this tile: nothing to do for any warp
+          sts_u4s(is + 16u, make_uint4(colmask, j_first, 0u, 0u));
           mbar_arrive_s(rs_s + kReadyOff + s * 8u);    // release: the stores above are visible to whoever observes the phase
         }
         __syncwarp();
