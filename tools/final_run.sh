@@ -1,9 +1,15 @@
-# Round-end measurement batch run under gpurun: tests, smoke, both bench arms, op sweep, ncu captures -> gpurun_out/s30_*
+# Round-end measurement batch run under gpurun: tests, smoke, both bench arms, op sweeps, ncu captures -> gpurun_out/r2_*
 set -x
-python -m pytest tests/ -m gpu -x -q > gpurun_out/s30_pytest.log 2>&1; tail -3 gpurun_out/s30_pytest.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/s30_smoke.log 2>&1; tail -1 gpurun_out/s30_smoke.log
-python bench.py --steps 3 --warmup 3 > gpurun_out/s30_bench.log 2> gpurun_out/s30_bench.err; tail -c 600 gpurun_out/s30_bench.log
-python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/s30_bench_ref.log 2> gpurun_out/s30_bench_ref.err; tail -c 400 gpurun_out/s30_bench_ref.log
-python tools/op_bench.py --tv --rois 512,2048 --json gpurun_out/s30_opbench.json > gpurun_out/s30_opbench.log 2>&1; tail -3 gpurun_out/s30_opbench.log
-python tools/profile_roi.py > gpurun_out/s30_plain_roi.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:msroi_.*tma -s 4 -c 2 -o gpurun_out/s30_roi -f python tools/profile_roi.py > gpurun_out/s30_ncu_roi.log 2>&1; tail -2 gpurun_out/s30_ncu_roi.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 1800 --csv --log-file gpurun_out/s30_launches_bench.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/s30_ncu_bench.log 2>&1; tail -2 gpurun_out/s30_ncu_bench.log; wc -l gpurun_out/s30_launches_bench.csv
+python -m pytest tests/ -m gpu -x -q > gpurun_out/r2_pytest.log 2>&1; tail -3 gpurun_out/r2_pytest.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; tail -1 gpurun_out/r2_smoke.log
+python bench.py --steps 3 --warmup 3 > gpurun_out/r2_bench.log 2> gpurun_out/r2_bench.err; tail -c 300 gpurun_out/r2_bench.log
+python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/r2_bench_ref.log 2> gpurun_out/r2_bench_ref.err; tail -c 300 gpurun_out/r2_bench_ref.log
+python bench.py --model fcos --steps 2 --warmup 2 --no-cpu-baseline > gpurun_out/r2_bench_fcos.log 2> gpurun_out/r2_bench_fcos.err; tail -c 300 gpurun_out/r2_bench_fcos.log
+python bench.py --domains 3 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_d3.log 2> gpurun_out/r2_bench_d3.err; tail -c 300 gpurun_out/r2_bench_d3.log
+python tools/op_bench.py --tv --ops roi --rois 512,1024,2048,4096,8192 --json gpurun_out/r2_opbench_roi_608.json > gpurun_out/r2_opbench_roi_608.log 2>&1; tail -2 gpurun_out/r2_opbench_roi_608.log
+python tools/op_bench.py --tv --ops roi --height 800 --width 1344 --rois 512,1024,2048,4096,8192 --json gpurun_out/r2_opbench_roi_800.json > gpurun_out/r2_opbench_roi_800.log 2>&1; tail -2 gpurun_out/r2_opbench_roi_800.log
+python tools/op_bench.py --tv --ops nms,match,fcos,rpn,grl,transform,sampler,fcos_post,grl_conv --json gpurun_out/r2_opbench_other.json > gpurun_out/r2_opbench_other.log 2>&1; tail -2 gpurun_out/r2_opbench_other.log
+python tools/bwd_check.py --algos 3,4 --iters 15 > gpurun_out/r2_bwd_check.log 2>&1; tail -2 gpurun_out/r2_bwd_check.log
+ncu --set full --clock-control none --import-source on -k regex:own_bwd -s 2 -c 1 -o gpurun_out/r2_own_bwd -f python tools/bwd_check.py --algos 4 --iters 2 > gpurun_out/r2_ncu_bwd.log 2>&1; tail -1 gpurun_out/r2_ncu_bwd.log
+ncu --set full --clock-control none --import-source on -k regex:msroi_fwd_tma -s 2 -c 1 -o gpurun_out/r2_fwd -f python tools/profile_roi.py > gpurun_out/r2_ncu_fwd.log 2>&1; tail -1 gpurun_out/r2_ncu_fwd.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 1800 --csv --log-file gpurun_out/r2_launches_bench.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2_ncu_bench.log 2>&1; tail -1 gpurun_out/r2_ncu_bench.log; wc -l gpurun_out/r2_launches_bench.csv
