@@ -113,4 +113,27 @@ static inline float float_round_down(double t) {
   return f;
 }
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with launch_pdl() may start while its predecessor in
+// the stream is still running; it must call pdl_wait() before touching anything the predecessor wrote (the call returns
+// when the predecessor grid has completed and its writes are visible).  pdl_trigger() in the predecessor lets the
+// dependent's CTAs be scheduled as soon as every predecessor CTA has called it (or exited) and resources allow — what
+// is saved is the launch latency and the dependent's prologue (barrier init, descriptor prefetch), a few us per boundary.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace dgod

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(kPlanWarps * 32)
 msroi_plan_kernel(const RoiDev g, const float* __restrict__ rois, int n_rois, RoiPlan* __restrict__ plans, int pix_bytes,
                   int want_ax) {
   __shared__ PlanScratch scratch[kPlanWarps];
+  pdl_trigger();                           // the streaming kernel may be scheduled behind this grid's CTAs (it waits for the plans)
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int k = blockIdx.x * kPlanWarps + w;
   if (k >= n_rois) return;
@@ -315,10 +316,32 @@ msroi_fwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, int n_ro
       mbar_init(&f.empty[i], NC / 32);
     }
     mbar_fence_init();
+    pdl_wait();                            // launched behind the plan kernel (programmatic dependent launch)
     mbar_expect_tx(&f.plan_full, kPlanFwdBytes);
     bulk_load_hint(smem + RING, plans + k, kPlanFwdBytes, &f.plan_full, policy_evict_first());
   }
   __syncthreads();
+  if (tid >= NC && tid - NC < kStagesMax) {
+    // Producer lanes: the first row of every ring stage is requested from the plan's header in GLOBAL memory (two loads)
+    // while the plan's own bulk copy into shared memory is still in flight — the consumers' first wait shrinks by the
+    // difference between a bulk-copy round trip + barrier wake-up and a plain load.  (Thread 0 executed pdl_wait()
+    // before the barrier above: the plan kernel's writes are visible to the whole grid.)
+    const RoiPlan* __restrict__ gp = plans + k;
+    const int4 h0 = __ldcg(reinterpret_cast<const int4*>(gp));          // n_rows, row_px, slot_mode, n_slots
+    const int lane = tid - NC;
+    if (h0.x > 0 && !h0.z) {
+      const int4 h1 = __ldcg(reinterpret_cast<const int4*>(gp) + 1);    // level, batch, x_first, inv_count
+      const unsigned row_bytes = (unsigned)h0.y * PIX;
+      const int n_stage = min(kStagesMax, RING / (int)row_bytes);
+      if (lane < n_stage && lane < h0.x) {
+        const int row = (int)__ldcg(&gp->rows[lane]);
+        const int W = g.W[h1.x];
+        const T* __restrict__ src = reinterpret_cast<const T*>(g.feat[h1.x]) + ((size_t)h1.y * g.H[h1.x] * W + (size_t)row * W + h1.z) * C;
+        mbar_expect_tx(&f.full[lane], row_bytes);
+        bulk_load_hint(ring + (size_t)lane * row_bytes, src, row_bytes, &f.full[lane], policy_evict_last());
+      }
+    }
+  }
   mbar_wait(&f.plan_full, 0u);
   const int n_rows = P.n_rows;
   const float inv = P.inv_count;
@@ -342,8 +365,8 @@ msroi_fwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, int n_ro
         if (lane < n_stage) {
           const T* __restrict__ span0 = img + (size_t)P.x_first * C;
           const int st = lane;
-          for (int i = st; i < n_rows; i += n_stage) {
-            if (i >= n_stage) mbar_wait(&f.empty[st], (unsigned)(i / n_stage - 1) & 1u);
+          for (int i = st + n_stage; i < n_rows; i += n_stage) {        // row st itself was requested above
+            mbar_wait(&f.empty[st], (unsigned)(i / n_stage - 1) & 1u);
             mbar_expect_tx(&f.full[st], row_bytes);
             bulk_load_hint(ring + (size_t)st * row_bytes, span0 + (size_t)P.rows[i] * W * C, row_bytes, &f.full[st], keep);
           }
@@ -736,7 +759,8 @@ static int launch_fwd_tma(const RoiDev& g, const float* rois, int n_rois, void* 
   }
   int rc = launch_plan(g, rois, n_rois, plans, C * (int)sizeof(T), 0, st);
   if (rc) return rc;
-  msroi_fwd_tma_kernel<T, C, SR><<<n_rois, C / 2 + 32, kSmem, st>>>(g, plans, n_rois, (T*)out);
+  DGOD_CUDA(launch_pdl(msroi_fwd_tma_kernel<T, C, SR>, dim3(n_rois), dim3(C / 2 + 32), (size_t)kSmem, st, g, (const RoiPlan*)plans, n_rois,
+                       (T*)out));
   DGOD_LAUNCHED();
   return DGOD_OK;
 }
