@@ -62,11 +62,15 @@ __device__ __forceinline__ bool iou_gt_exact(const float4 a, float area_a, const
 __global__ void __launch_bounds__(256)
 nms_mask_kernel(const float4* __restrict__ sbox, const uint32_t* __restrict__ runkey, int n_pos,
                 float thr, unsigned long long* __restrict__ mask, int row_words,
-                unsigned long long* __restrict__ diag_cols) {
+                unsigned long long* __restrict__ diag_cols, int pdl) {
   __shared__ float4 s_box[kMaskChunksPerCta][64];
   __shared__ float s_area[kMaskChunksPerCta][64];
   __shared__ uint32_t s_key[kMaskChunksPerCta][64];
   __shared__ uint32_t s_colbits[64][2];
+  if (pdl) {                                                  // launched behind the kernel that wrote sbox / runkey
+    pdl_wait();
+    pdl_trigger();
+  }
   const int r = blockIdx.x;                                   // row chunk
   const int c0 = r + kMaskChunksPerCta * blockIdx.y;          // first column chunk of this CTA
   const int row0 = r * 64;
@@ -143,7 +147,13 @@ int launch_nms_mask(const float4* sbox, const uint32_t* runkey, int n_pos, int m
   // a run of length L starting anywhere inside row chunk r reaches column chunk r + L/64 + 1 at most
   const int groups = (row_words + kMaskChunksPerCta - 1) / kMaskChunksPerCta;
   dim3 grid(cdiv(n_pos, 64), groups);
-  nms_mask_kernel<<<grid, 256, 0, st>>>(sbox, runkey, n_pos, thr, mask, row_words, diag_cols);
+  // Programmatic dependent launch pays for grids of a few waves (it hides the launch gap, ~4 us); griddepcontrol.wait
+  // itself costs every CTA ~2 us, which a grid of a hundred waves (100 000 boxes) would pay a hundred times.
+  if ((long long)grid.x * grid.y <= 16384) {
+    DGOD_CUDA(launch_pdl(nms_mask_kernel, grid, dim3(256), 0, st, sbox, runkey, n_pos, thr, mask, row_words, diag_cols, 1));
+  } else {
+    nms_mask_kernel<<<grid, 256, 0, st>>>(sbox, runkey, n_pos, thr, mask, row_words, diag_cols, 0);
+  }
   DGOD_LAUNCHED();
   return DGOD_OK;
 }
@@ -172,6 +182,8 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
                 int row_words, int depth, const uint32_t* __restrict__ runkey, const uint8_t* __restrict__ alive,
                 int n_pos, unsigned long long* __restrict__ keepbits, int32_t* __restrict__ compact_pos,
                 int32_t* __restrict__ run_count) {
+  pdl_wait();                                                 // launched behind the mask kernel
+  pdl_trigger();
   extern __shared__ __align__(128) unsigned long long s_dyn[];     // ring[depth][64][row_words] | removed[row_words]
   const size_t buf_words = (size_t)64 * row_words;
   unsigned long long* s_removed = s_dyn + (size_t)depth * buf_words;
@@ -434,8 +446,8 @@ int launch_nms_scan(const unsigned long long* mask, const unsigned long long* di
       DGOD_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_smem = smem;
     }
-    nms_scan_kernel<<<cdiv(n_pos, 64), kScanThreads, smem, st>>>(mask, diag_cols, row_words, depth, runkey, alive, n_pos,
-                                                               keepbits, compact_pos, run_count);
+    DGOD_CUDA(launch_pdl(nms_scan_kernel, dim3(cdiv(n_pos, 64)), dim3(kScanThreads), smem, st, mask, diag_cols, row_words, depth, runkey,
+                         alive, n_pos, keepbits, compact_pos, run_count));
   } else {
     const size_t smem = (size_t)row_words * sizeof(unsigned long long);
     static size_t attr_smem_long = 0;
@@ -443,6 +455,7 @@ int launch_nms_scan(const unsigned long long* mask, const unsigned long long* di
       DGOD_CUDA(cudaFuncSetAttribute(nms_scan_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_smem_long = smem;
     }
+    // (a plain launch: behind a mask kernel of many waves, early-scheduled 1024-thread CTAs cost more than the launch gap)
     nms_scan_long_kernel<<<cdiv(n_pos, 64), kScanThreadsLong, smem, st>>>(mask, diag_cols, row_words, runkey, alive, n_pos,
                                                                         keepbits, compact_pos, run_count);
   }
@@ -621,6 +634,7 @@ nms_order_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
                  const uint8_t* __restrict__ valid, const int32_t* __restrict__ seg_offsets, int offset_mode,
                  unsigned long long* __restrict__ skey, float4* __restrict__ sbox, uint32_t* __restrict__ runkey,
                  unsigned long long* __restrict__ keepbits, int32_t* __restrict__ seg_status) {
+  pdl_trigger();                                              // the mask kernel may be scheduled behind this grid
   extern __shared__ __align__(16) unsigned long long s_all[];
   __shared__ uint32_t s_max;
   cg::cluster_group cluster = cg::this_cluster();
@@ -692,6 +706,8 @@ nms_emit_kernel(const unsigned long long* __restrict__ skey, const unsigned long
                 const int32_t* __restrict__ seg_offsets, const int32_t* __restrict__ seg_status, int n_seg,
                 int out_stride, int64_t* __restrict__ keep_out, int32_t* __restrict__ keep_count,
                 int32_t* __restrict__ status) {
+  pdl_wait();                                                 // launched behind the mask kernel
+  pdl_trigger();
   extern __shared__ __align__(16) unsigned long long s_all[];
   __shared__ int s_count;
   cg::cluster_group cluster = cg::this_cluster();
@@ -816,8 +832,9 @@ extern "C" int dgod_nms_batched(const float* boxes, const float* scores, const i
     if (rc) return rc;
     rc = launch_nms_scan(b.mask, b.diag_cols, b.runkey, nullptr, n_total, max_seg_len, b.keepbits, nullptr, nullptr, st);
     if (rc) return rc;
-    nms_emit_kernel<<<n_seg * kSegCluster, kSegSortThreads, smem, st>>>(b.keys, b.keepbits, seg_offsets, b.seg_live, n_seg, out_stride,
-                                                         keep_out, keep_count, status);
+    DGOD_CUDA(launch_pdl(nms_emit_kernel, dim3(n_seg * kSegCluster), dim3(kSegSortThreads), smem, st, (const unsigned long long*)b.keys,
+                         (const unsigned long long*)b.keepbits, seg_offsets, (const int32_t*)b.seg_live, n_seg, out_stride, keep_out, keep_count,
+                         status));
     DGOD_LAUNCHED();
     return DGOD_OK;
   }

@@ -158,6 +158,7 @@ rpn_topk_decode_kernel(const RpnDev g, const float* __restrict__ proposals_flat,
                        const float* __restrict__ image_sizes, int kp_max, int cache_keys, float4* __restrict__ sbox,
                        float* __restrict__ cscore, uint8_t* __restrict__ alive,
                        uint32_t* __restrict__ runkey) {
+  pdl_trigger();                                              // the mask kernel may be scheduled behind this grid
   extern __shared__ unsigned long long s_sel[];  // kp_max records: ~ordered(logit):32 | r:32, then the key cache
   uint32_t* s_keys = reinterpret_cast<uint32_t*>(s_sel + kp_max);
   __shared__ SelShared s_sh;
@@ -341,6 +342,7 @@ rpn_merge_kernel(const RpnDev g, int post_nms_top_n, const float4* __restrict__ 
                  const float* __restrict__ cscore, const int32_t* __restrict__ compact_pos,
                  const int32_t* __restrict__ run_count, float* __restrict__ out_boxes,
                  float* __restrict__ out_scores, int32_t* __restrict__ out_count) {
+  pdl_wait();                                                 // launched behind the scan kernel
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   {
@@ -467,8 +469,8 @@ static int rpn_run(const dgod_rpn_config* cfg, RpnDev& g, const float* proposals
   if (rc) return rc;
   rc = launch_nms_scan(b.mask, b.diag_cols, b.runkey, b.alive, n_pos, max_k, nullptr, b.compact, b.run_count, st);
   if (rc) return rc;
-  rpn_merge_kernel<<<dim3(cdiv(g.k_tot, 256), g.n_img), 256, 0, st>>>(
-      g, cfg->post_nms_top_n, b.sbox, b.cscore, b.compact, b.run_count, out_boxes, out_scores, out_count);
+  DGOD_CUDA(launch_pdl(rpn_merge_kernel, dim3(cdiv(g.k_tot, 256), g.n_img), dim3(256), 0, st, g, cfg->post_nms_top_n, (const float4*)b.sbox,
+                       (const float*)b.cscore, (const int32_t*)b.compact, (const int32_t*)b.run_count, out_boxes, out_scores, out_count));
   DGOD_LAUNCHED();
   return DGOD_OK;
 }
