@@ -88,6 +88,7 @@ fcos_loss_fwd_kernel(const float* __restrict__ cls_logits, const float* __restri
                      const float* __restrict__ ctrness, const float* __restrict__ anchors,
                      const int64_t* __restrict__ cls_targets, const float* __restrict__ box_targets, long long total,
                      int n_anchors, int C, float alpha, double* __restrict__ partial) {
+  pdl_trigger();                                             // the one-block finish kernel is scheduled behind this grid
   const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double cls = 0.0, reg = 0.0, ctr = 0.0, fg = 0.0;
   if (o < total) {
@@ -131,6 +132,7 @@ fcos_loss_fwd_kernel(const float* __restrict__ cls_logits, const float* __restri
 __global__ void __launch_bounds__(kLossThreads)
 fcos_loss_finish_kernel(const double* __restrict__ partial, int n_blocks, float* __restrict__ out) {
   __shared__ double s[4][kLossThreads];
+  pdl_wait();                                                // launched behind fcos_loss_fwd_kernel (programmatic dependent launch)
   double v[4] = {0.0, 0.0, 0.0, 0.0};
   for (int b = threadIdx.x; b < n_blocks; b += kLossThreads)
 #pragma unroll
@@ -214,7 +216,8 @@ extern "C" int dgod_fcos_loss_fwd(const float* cls_logits, const float* bbox_reg
         (double*)workspace);
     DGOD_LAUNCHED();
   }
-  fcos_loss_finish_kernel<<<1, kLossThreads, 0, (cudaStream_t)stream>>>((const double*)workspace, n_blocks, losses);
+  DGOD_CUDA(launch_pdl(fcos_loss_finish_kernel, dim3(1), dim3(kLossThreads), 0, (cudaStream_t)stream, (const double*)workspace, n_blocks,
+                       losses));
   DGOD_LAUNCHED();
   return DGOD_OK;
 }
