@@ -165,7 +165,11 @@ rpn_topk_decode_kernel(const RpnDev g, const float* __restrict__ proposals_flat,
   __shared__ int s_count;
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
-  const int l = blockIdx.x / kTopkCluster, b = blockIdx.y;
+  // x = (image, cluster rank), y = level: clusters are scheduled level by level, the finest (largest) level of every image
+  // first.  An SM holds one CTA of this kernel, so ~15 clusters are resident at a time (ncu: launch__cluster_max_active):
+  // in (level, image)-fastest order every one of the three waves contained a 116 k-anchor level; now the first wave
+  // holds the large levels and the small ones fill the slots they free.
+  const int l = blockIdx.y, b = blockIdx.x / kTopkCluster;
   const int n = g.n_l[l], k = g.k_l[l], A = g.A;
   const int HW = g.H[l] * g.W[l];
   const float* __restrict__ obj =
@@ -462,7 +466,7 @@ static int rpn_run(const dgod_rpn_config* cfg, RpnDev& g, const float* proposals
   }
   // no memset: every (image, level) is a run (k_l >= 1), so the scan writes every run_count the merge reads, and the
   // merge zero-fills the output rows behind each image's count
-  rpn_topk_decode_kernel<<<dim3(g.n_levels * kTopkCluster, g.n_img), kTopkThreads, smem, st>>>(
+  rpn_topk_decode_kernel<<<dim3(g.n_img * kTopkCluster, g.n_levels), kTopkThreads, smem, st>>>(
       g, proposals_flat, objectness_flat, image_sizes, kp, cache_keys, b.sbox, b.cscore, b.alive, b.runkey);
   DGOD_LAUNCHED();
   int rc = launch_nms_mask(b.sbox, b.runkey, n_pos, max_k, float_round_down(cfg->nms_thresh), b.mask, b.diag_cols, st);
