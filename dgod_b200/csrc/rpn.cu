@@ -22,7 +22,7 @@ namespace cg = cooperative_groups;
 
 namespace dgod {
 
-constexpr int kTopkThreads = 1024;
+constexpr int kTopkThreads = 512;    // 2 CTAs per SM (1024 threads: one, i.e. ~15 resident clusters and three waves at B=8 x 5 levels)
 constexpr int kTopkCluster = 8;        // CTAs (one cluster) sharing the objectness of one (level, image)
 constexpr int kSelUnroll = 8;          // independent loads in flight per thread in the selection passes
 
