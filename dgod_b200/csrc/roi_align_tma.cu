@@ -321,24 +321,49 @@ msroi_fwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, int n_ro
     bulk_load_hint(smem + RING, plans + k, kPlanFwdBytes, &f.plan_full, policy_evict_first());
   }
   __syncthreads();
-  if (tid >= NC && tid - NC < kStagesMax) {
-    // Producer lanes: the first row of every ring stage is requested from the plan's header in GLOBAL memory (two loads)
-    // while the plan's own bulk copy into shared memory is still in flight — the consumers' first wait shrinks by the
-    // difference between a bulk-copy round trip + barrier wake-up and a plain load.  (Thread 0 executed pdl_wait()
-    // before the barrier above: the plan kernel's writes are visible to the whole grid.)
+  if (tid >= NC) {
+    // Producer warp: the first row of every ring stage is requested from the plan's header in GLOBAL memory (a few
+    // independent loads) while the plan's own bulk copy into shared memory is still in flight — the consumers' first
+    // wait shrinks by the difference between a bulk-copy round trip + barrier wake-up and a plain load.  (Thread 0
+    // executed pdl_wait() before the barrier above: the plan kernel's writes are visible to the whole grid.)
     const RoiPlan* __restrict__ gp = plans + k;
     const int4 h0 = __ldcg(reinterpret_cast<const int4*>(gp));          // n_rows, row_px, slot_mode, n_slots
     const int lane = tid - NC;
-    if (h0.x > 0 && !h0.z) {
+    if (h0.x > 0) {
       const int4 h1 = __ldcg(reinterpret_cast<const int4*>(gp) + 1);    // level, batch, x_first, inv_count
       const unsigned row_bytes = (unsigned)h0.y * PIX;
       const int n_stage = min(kStagesMax, RING / (int)row_bytes);
-      if (lane < n_stage && lane < h0.x) {
-        const int row = (int)__ldcg(&gp->rows[lane]);
-        const int W = g.W[h1.x];
-        const T* __restrict__ src = reinterpret_cast<const T*>(g.feat[h1.x]) + ((size_t)h1.y * g.H[h1.x] * W + (size_t)row * W + h1.z) * C;
-        mbar_expect_tx(&f.full[lane], row_bytes);
-        bulk_load_hint(ring + (size_t)lane * row_bytes, src, row_bytes, &f.full[lane], policy_evict_last());
+      const int W = g.W[h1.x];
+      const T* __restrict__ img = reinterpret_cast<const T*>(g.feat[h1.x]) + (size_t)h1.y * g.H[h1.x] * W * C;
+      const unsigned long long keep = policy_evict_last();
+      if (!h0.z) {
+        if (lane < n_stage && lane < h0.x) {
+          const int row = (int)__ldcg(&gp->rows[lane]);
+          mbar_expect_tx(&f.full[lane], row_bytes);
+          bulk_load_hint(ring + (size_t)lane * row_bytes, img + ((size_t)row * W + h1.z) * C, row_bytes, &f.full[lane], keep);
+        }
+      } else {
+        // slot mode: lane sx issues its 1-2 pixel piece of the first n_stage rows
+        int so = -1, two = 0, sx0 = 0;
+        if (lane < NS) {
+          so = (int)__ldcg(&gp->slot_of[lane]);
+          two = (int)__ldcg(&gp->slot_two[lane]);
+          sx0 = (int)__ldcg(&gp->slot_x[lane]);
+        }
+        const int4 r03 = __ldcg(reinterpret_cast<const int4*>(gp->rows));          // rows 0..7 (kStagesMax)
+        const unsigned vm = __ballot_sync(0xffffffffu, so >= 0), tm = __ballot_sync(0xffffffffu, so >= 0 && two);
+        const unsigned slot_total = (unsigned)(__popc(vm) + __popc(tm)) * PIX;
+        const int first = __ffs(vm) - 1;
+        const int n_early = min(n_stage, h0.x);
+        if (so >= 0) {
+          const unsigned bytes = two ? 2u * PIX : (unsigned)PIX;
+          const int rw[4] = {r03.x, r03.y, r03.z, r03.w};
+          for (int i = 0; i < n_early; ++i) {
+            const int row = (int)(short)((unsigned)rw[i >> 1] >> (16 * (i & 1)));
+            if (lane == first) mbar_expect_tx(&f.full[i], slot_total);
+            bulk_load_hint(ring + (size_t)i * row_bytes + (size_t)so * 2 * PIX, img + ((size_t)row * W + sx0) * C, bytes, &f.full[i], keep);
+          }
+        }
       }
     }
   }
@@ -382,10 +407,12 @@ msroi_fwd_tma_kernel(const RoiDev g, const RoiPlan* __restrict__ plans, int n_ro
         const unsigned bytes = P.slot_two[lane] ? 2u * PIX : (unsigned)PIX;
         const size_t dst_off = (size_t)P.slot_of[lane] * 2 * PIX;
         const T* __restrict__ src0 = img + (size_t)P.slot_x[lane] * C;
-        int st = 0;
-        unsigned phase = 1u;                 // toggles per lap: lap L >= 1 waits for the (L-1)-th release of its stage
-        for (int i = 0; i < n_rows; ++i) {
-          if (i >= n_stage) mbar_wait(&f.empty[st], phase);
+        // rows 0 .. n_early-1 were requested above
+        const int n_early = min(n_stage, n_rows);
+        int st = n_early == n_stage ? 0 : n_early;
+        unsigned phase = n_early == n_stage ? 0u : 1u;   // toggles per lap: lap L >= 1 waits for the (L-1)-th release of its stage
+        for (int i = n_early; i < n_rows; ++i) {
+          mbar_wait(&f.empty[st], phase);
           // the expected byte count may be posted after some pieces have landed: the phase cannot complete before
           // this arrival
           if (lane == first) mbar_expect_tx(&f.full[st], slot_total);

@@ -368,20 +368,32 @@ rpn_merge_kernel(const RpnDev g, int post_nms_top_n, const float4* __restrict__ 
   const size_t img0 = (size_t)b * g.k_tot;
   const int pos = compact_pos[img0 + g.c_off[l] + j];
   const float s = cscore[pos];
+  // rank = own position + the number of entries of every other level that sort before this one: the binary searches of
+  // the other levels run in lockstep (their dependent load pairs are in flight together: one chain of log2(k) round trips
+  // instead of one per level)
   int rank = j;
-  for (int o = 0; o < g.n_levels; ++o) {
-    if (o == l) continue;
-    const int cnt = run_count[b * DGOD_MAX_LEVELS + o];
-    const int32_t* lst = compact_pos + img0 + g.c_off[o];
-    int lo = 0, hi = cnt;  // scores along lst are non-increasing
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      const float v = cscore[lst[mid]];
-      const bool before = o < l ? (v >= s) : (v > s);
-      if (before) lo = mid + 1; else hi = mid;
-    }
-    rank += lo;
+  int lo[DGOD_MAX_LEVELS], len[DGOD_MAX_LEVELS];
+  int longest = 0;
+#pragma unroll
+  for (int o = 0; o < DGOD_MAX_LEVELS; ++o) {
+    lo[o] = 0;
+    len[o] = (o < g.n_levels && o != l) ? run_count[b * DGOD_MAX_LEVELS + o] : 0;
+    longest = max(longest, len[o]);
   }
+  for (int it = longest; it > 0; it >>= 1) {             // floor(log2(longest)) + 1 halvings settle every search
+#pragma unroll
+    for (int o = 0; o < DGOD_MAX_LEVELS; ++o) {
+      if (len[o] > 0) {                                   // scores along a level's list are non-increasing
+        const int half = len[o] >> 1;
+        const float v = cscore[compact_pos[img0 + g.c_off[o] + lo[o] + half]];
+        const bool before = o < l ? (v >= s) : (v > s);
+        lo[o] = before ? lo[o] + half + 1 : lo[o];
+        len[o] = before ? len[o] - half - 1 : half;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < DGOD_MAX_LEVELS; ++o) rank += lo[o];
   if (rank < post_nms_top_n) {
     reinterpret_cast<float4*>(out_boxes)[(size_t)b * post_nms_top_n + rank] = sbox[pos];
     out_scores[(size_t)b * post_nms_top_n + rank] = s;
