@@ -20,8 +20,9 @@
 //                    bin such that all its weights sit on 4 consecutive bins (3 of 4 RoIs have one) ->
 //                    a 2 560-byte plan; plus a 16-byte record (level, image, footprint box).
 //   own_bin_kernel   one warp per tile: the RoIs (index order) whose footprint box meets the tile.
-//   own_bwd_kernel   persistent, one CTA per SM, 16 warps, work items (tile x 64-channel slice) dealt
-//                    round-robin with the coarse levels first.  Warp roles:
+//   own_bwd_kernel   persistent, one CTA per SM, 16 warps, work items (tile x 64-channel slice) claimed from a
+//                    global counter, coarse levels first (a CTA whose SM was still held by another stream's
+//                    kernel — an NCCL all-reduce overlapping backward — just takes fewer).  Warp roles:
 //                      producer  lane 0 streams (plan, [64][49] gradient slice) pairs through a ring of 15
 //                                stages with two tensor-map loads per stage (cp.async.bulk.tensor, SASS
 //                                UTMALDG; completion counted in bytes on the stage's `full` mbarrier);
@@ -68,6 +69,7 @@ constexpr int kBlk = 4;                // the consumers sweep a tile row in bloc
 constexpr int kTaps = 4;               // ... whose weights sit on 4 consecutive bins (else the general 7-bin form runs)
 constexpr int kMaxBlk = 8;             // blocks a span of <= 28 columns can meet
 constexpr int kOwnTable = 0x40000000;  // PairInfo::w_off: the weights are in PairInfo::wtab, not in the plan
+constexpr int kItemRing = 8;           // claims the producer may be ahead of the slowest warp of its CTA
 constexpr int kCounterBytes = 73728;   // [0] pair cursor; +1024: per-CTA, per-warp cycle counters of DGOD_OWN_TIMING builds
 
 struct alignas(128) Plan {
@@ -151,7 +153,7 @@ own_plan_kernel(const RoiDev g, const float* __restrict__ rois, int n_rois, Plan
                 int* __restrict__ cursor) {
   __shared__ Scratch scratch[kPlanWarps];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *cursor = 0;      // the bin kernel (next in the stream) counts pairs from zero
+  if (blockIdx.x == 0 && threadIdx.x == 0) { cursor[0] = 0; cursor[4] = 0; }   // pair cursor of the bin kernel, work counter of the main kernel
   const int k = blockIdx.x * kPlanWarps + w;
   if (k >= n_rois) return;
   Scratch& t = scratch[w];
@@ -405,11 +407,17 @@ __device__ __forceinline__ void column_block_any(unsigned blocks, unsigned w, co
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1)
 own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorMap tm_plan, const __grid_constant__ CUtensorMap tm_g,
-               const int2* __restrict__ tile_list, const int* __restrict__ pair_k, long long* __restrict__ timing) {
+               const int2* __restrict__ tile_list, const int* __restrict__ pair_k, int* __restrict__ work_counter,
+               long long* __restrict__ timing) {
   constexpr int NS = Cfg<T>::kStages;
   constexpr int SB = Cfg<T>::kStageBytes;
   extern __shared__ __align__(128) unsigned char smem[];
-  struct alignas(16) RingSync { PairInfo info[NS]; unsigned long long full[NS], ready[NS], empty[NS]; };
+  // item_*: the work items this CTA has claimed (item id, first pair, pairs), published by the producer for the other warps
+  struct alignas(16) RingSync {
+    PairInfo info[NS];
+    int4 item[kItemRing];
+    unsigned long long full[NS], ready[NS], empty[NS], item_full[kItemRing], item_empty[kItemRing];
+  };
   __shared__ RingSync rs;
   PairInfo* const info = rs.info;
   unsigned long long* const full = rs.full;
@@ -427,6 +435,11 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
       mbar_init(&ready[i], 1);
       mbar_init(&empty[i], kWarps);
     }
+#pragma unroll
+    for (int i = 0; i < kItemRing; ++i) {
+      mbar_init(&rs.item_full[i], 1);
+      mbar_init(&rs.item_empty[i], kWarps + 1);
+    }
     mbar_fence_init();
     tmap_prefetch(&tm_plan);
     tmap_prefetch(&tm_g);
@@ -435,7 +448,8 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
   // 32-bit shared-window addresses of the ring's bookkeeping, computed once and opaque to the compiler
   const unsigned rs_s = smem_opaque(&rs), smem_s = smem_opaque(smem);
   constexpr unsigned kFullOff = (unsigned)offsetof(RingSync, full), kReadyOff = (unsigned)offsetof(RingSync, ready),
-                     kEmptyOff = (unsigned)offsetof(RingSync, empty);
+                     kEmptyOff = (unsigned)offsetof(RingSync, empty), kItemOff = (unsigned)offsetof(RingSync, item),
+                     kItemFullOff = (unsigned)offsetof(RingSync, item_full), kItemEmptyOff = (unsigned)offsetof(RingSync, item_empty);
 
   if (warp == kWarps) {
     // ------------------------------------------------------------------ producer.  Walks the pair lists of this CTA's
@@ -444,31 +458,42 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
     // ahead as the ring allows.
     const int rows_per_roi = C / kCS * Cfg<T>::kGBoxRows;
     unsigned s = 0, phase = 0, q = 0;
-    int n_claimed = 0;
-    auto claim = [&]() -> int {
-      const int it = (int)blockIdx.x + n_claimed * (int)gridDim.x;
-      ++n_claimed;
-      return it < n_items ? it : -1;
-    };
-    int it = claim();
-    int2 lc = make_int2(0, 0);
-    int kk = 0;
-    if (it >= 0) {
-      lc = __ldg(tile_list + it / tg.n_slices);
-      kk = lane < lc.y ? __ldg(pair_k + lc.x + lane) : 0;
-    }
-    while (it >= 0) {
-      const int sl = it % tg.n_slices;
-      const int it_next = claim();
-      int2 lc_next = make_int2(0, 0);
-      int kk_next = 0;
-      if (it_next >= 0) {
-        lc_next = __ldg(tile_list + it_next / tg.n_slices);
-        kk_next = lane < lc_next.y ? __ldg(pair_k + lc_next.x + lane) : 0;
+    // Work items are CLAIMED, not dealt: the first one is blockIdx.x, the following ones come from a global counter in index
+    // order (coarse levels first).  A CTA that starts late — its SM was still busy with another stream's kernel, e.g. an NCCL
+    // all-reduce overlapping this backward — or that drew heavier items simply takes fewer of them.  Three claims are in
+    // flight: [2] its atomic is outstanding, [1] its pair-list header is loading, [0] ready to issue; every claim is
+    // published in the item ring for the decoder and the consumers.
+    auto draw = [&]() -> int { return lane == 0 ? atomicAdd(work_counter, 1) + (int)gridDim.x : 0; };
+    auto settle = [&](int raw) -> int { const int v = __shfl_sync(0xffffffffu, raw, 0); return v < n_items ? v : -1; };
+    auto header = [&](int it) -> int2 { return it >= 0 ? __ldg(tile_list + it / tg.n_slices) : make_int2(0, 0); };
+    int it0 = (int)blockIdx.x < n_items ? (int)blockIdx.x : -1;
+    int raw1 = draw();
+    int2 lc0 = header(it0);
+    int it1 = settle(raw1);
+    int raw2 = it1 >= 0 ? draw() : n_items;
+    int2 lc1 = header(it1);
+    int kk0 = lane < lc0.y ? __ldg(pair_k + lc0.x + lane) : 0;
+    unsigned n_pub = 0;
+    while (true) {
+      const int it2 = settle(raw2);
+      raw2 = it2 >= 0 ? draw() : n_items;
+      const int2 lc2 = header(it2);
+      const int kk1 = lane < lc1.y ? __ldg(pair_k + lc1.x + lane) : 0;
+      {
+        const unsigned j = n_pub % kItemRing;
+        if (lane == 0) {
+          if (n_pub >= (unsigned)kItemRing) mbar_wait_s(rs_s + kItemEmptyOff + j * 8u, ((n_pub / kItemRing) & 1u) ^ 1u);
+          sts_u4s(rs_s + kItemOff + j * 16u, make_uint4((unsigned)it0, (unsigned)lc0.x, (unsigned)lc0.y, 0u));
+          mbar_arrive_s(rs_s + kItemFullOff + j * 8u);          // release: the entry is visible to whoever observes the phase
+        }
+        ++n_pub;
       }
-      for (int p0 = 0; p0 < lc.y; p0 += 32) {
-        if (p0) kk = p0 + lane < lc.y ? __ldg(pair_k + lc.x + p0 + lane) : 0;
-        const int n = min(32, lc.y - p0);
+      if (it0 < 0) break;
+      const int sl = it0 % tg.n_slices;
+      int kk = kk0;
+      for (int p0 = 0; p0 < lc0.y; p0 += 32) {
+        if (p0) kk = p0 + lane < lc0.y ? __ldg(pair_k + lc0.x + p0 + lane) : 0;
+        const int n = min(32, lc0.y - p0);
         for (int i = 0; i < n; ++i, ++q) {
           const int k = __shfl_sync(0xffffffffu, kk, i);
           if (lane == 0) {
@@ -482,7 +507,8 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
         }
         __syncwarp();
       }
-      it = it_next; lc = lc_next; kk = kk_next;
+      it0 = it1; lc0 = lc1; kk0 = kk1;
+      it1 = it2; lc1 = lc2;
     }
     return;
   }
@@ -491,11 +517,16 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
     // ------------------------------------------------------------------ decoder: once per pair, intersects the RoI's live
     // rows / columns with the tile and publishes the result in info[stage]
     unsigned s = 0, phase = 0;
-    int2 lc_next = (int)blockIdx.x < n_items ? __ldg(tile_list + blockIdx.x / tg.n_slices) : make_int2(0, 0);
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    for (unsigned n_it = 0;; ++n_it) {
+      const unsigned jr = n_it % kItemRing;
+      mbar_wait_s(rs_s + kItemFullOff + jr * 8u, (n_it / kItemRing) & 1u);
+      const uint4 e = lds_u4(rs_s + kItemOff + jr * 16u);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_s(rs_s + kItemEmptyOff + jr * 8u);
+      if ((int)e.x < 0) break;
+      const int it = (int)e.x;
+      const int2 lc = make_int2((int)e.y, (int)e.z);
       const TileAt a = tile_at(tg, it / tg.n_slices);
-      const int2 lc = lc_next;
-      if (it + (int)gridDim.x < n_items) lc_next = __ldg(tile_list + (it + gridDim.x) / tg.n_slices);   // next item's list, early
       for (int p = 0; p < lc.y; ++p) {
         mbar_wait_s(rs_s + kFullOff + s * 8u, phase);
         const unsigned st_s = smem_s + s * (unsigned)SB;
@@ -574,12 +605,17 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
   long long t_wait = 0, t_store = 0;
 #endif
   unsigned s = 0, phase = 0;                                // ring position of pair q
-  int2 lc_next = (int)blockIdx.x < n_items ? __ldg(tile_list + blockIdx.x / tg.n_slices) : make_int2(0, 0);
-  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+  for (unsigned n_it = 0;; ++n_it) {
+    const unsigned jr = n_it % kItemRing;
+    mbar_wait_s(rs_s + kItemFullOff + jr * 8u, (n_it / kItemRing) & 1u);
+    const uint4 e = lds_u4(rs_s + kItemOff + jr * 16u);
+    __syncwarp();
+    if (lane == 0) mbar_arrive_s(rs_s + kItemEmptyOff + jr * 8u);
+    if ((int)e.x < 0) break;
+    const int it = (int)e.x;
+    const int2 lc = make_int2((int)e.y, (int)e.z);
     const int t_id = it / tg.n_slices, sl = it - t_id * tg.n_slices;
     const TileAt a = tile_at(tg, t_id);
-    const int2 lc = lc_next;
-    if (it + (int)gridDim.x < n_items) lc_next = __ldg(tile_list + (it + gridDim.x) / tg.n_slices);   // next item's list, early
     float2 acc[kRPW][kTileW];
 #pragma unroll
     for (int r = 0; r < kRPW; ++r)
@@ -803,7 +839,7 @@ static int launch_own(const RoiDev& g, const own::Tiles& tg, const OwnLayout& L,
     own::own_plan_kernel<<<cdiv(n_rois, own::kPlanWarps), own::kPlanWarps * 32, 0, st>>>(g, rois, n_rois, plans, bins, cursor);
     DGOD_LAUNCHED();
   } else {
-    DGOD_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int), st));
+    DGOD_CUDA(cudaMemsetAsync(cursor, 0, 8 * sizeof(int), st));
   }
   own::own_bin_kernel<<<cdiv(tg.n_tiles, own::kBinWarps), own::kBinWarps * 32, 0, st>>>(tg, bins, n_rois, roi_img_offsets, tile_list,
                                                                                       pair_k, cursor);
@@ -823,7 +859,7 @@ static int launch_own(const RoiDev& g, const own::Tiles& tg, const OwnLayout& L,
                          CF::kGBoxRows);
     if (rc) return rc;
   }
-  own::own_bwd_kernel<T><<<grid, own::kThreads, own::Cfg<T>::kSmem, st>>>(g, tg, tm_plan, tm_g, tile_list, pair_k,
+  own::own_bwd_kernel<T><<<grid, own::kThreads, own::Cfg<T>::kSmem, st>>>(g, tg, tm_plan, tm_g, tile_list, pair_k, cursor + 4,
                                                                        reinterpret_cast<long long*>(ws + 1024));
   DGOD_LAUNCHED();
   return DGOD_OK;
