@@ -175,7 +175,7 @@ int msroi_bwd_tma(const dgod_roi_config* cfg, const RoiDev& g, const void* grad_
 size_t msroi_tma_workspace(int n_rois);
 // owner-computes backward (roi_align_own.cu): channels_last, 7x7 bins, sampling ratio 1..2, C % 64 == 0
 int msroi_bwd_own(const dgod_roi_config* cfg, const RoiDev& g, const void* grad_out, const float* rois, int n_rois,
-                  const int32_t* roi_img_offsets, void* workspace, size_t workspace_bytes, cudaStream_t st, int* handled);
+                  const int32_t* roi_img_offsets, void* workspace, size_t workspace_bytes, cudaStream_t st, int* handled, int claim);
 size_t msroi_own_workspace(const RoiDev& g, int n_rois);
 
 // DGOD_FWD_ALGO=1 keeps the forward on the table-driven kernel (A/B measurements); default: TMA path first.
@@ -250,7 +250,7 @@ extern "C" int dgod_msroi_align_bwd(const dgod_roi_config* cfg, const void* grad
   int rc = fill_roi_dev(cfg, g);
   if (rc) return rc;
   DGOD_REQUIRE(n_rois >= 0, "roi_align: negative n_rois");
-  DGOD_REQUIRE(algo >= 0 && algo <= 4, "roi_align: unknown backward algorithm");
+  DGOD_REQUIRE(algo >= 0 && algo <= 5, "roi_align: unknown backward algorithm");
   DGOD_REQUIRE(grad_feats, "roi_align: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t esz = cfg->dtype == DGOD_F32 ? 4 : 2;
@@ -264,9 +264,11 @@ extern "C" int dgod_msroi_align_bwd(const dgod_roi_config* cfg, const void* grad
   // workspace was sized with dgod_msroi_align_bwd_workspace_bytes_cfg; else the TMA bulk-reduce path; else
   // fp32 gradients take the scatter path (16-byte vector reductions on channels_last, scalar atomics
   // on NCHW) and bf16 gradients the deterministic tile gather (fp32 accumulation, one rounding).
-  if (algo == 0 || algo == 4) {
+  if (algo == 0 || algo == 4 || algo == 5) {
+    // 4: work items dealt round-robin (the default); 5: claimed from a global counter — for steps in which other
+    // streams' kernels (an NCCL all-reduce overlapping backward) hold SMs when this persistent grid starts
     int handled = 0;
-    rc = msroi_bwd_own(cfg, g, grad_out, rois, n_rois, roi_img_offsets, workspace, workspace_bytes, st, &handled);
+    rc = msroi_bwd_own(cfg, g, grad_out, rois, n_rois, roi_img_offsets, workspace, workspace_bytes, st, &handled, algo == 5);
     if (rc || handled) return rc;
     DGOD_REQUIRE(algo == 0, "roi_align: the owner-computes backward does not support this configuration or workspace");
   }

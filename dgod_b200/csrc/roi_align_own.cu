@@ -404,7 +404,8 @@ __device__ __forceinline__ void column_block_any(unsigned blocks, unsigned w, co
   }
 }
 
-template <typename T>
+// kClaim: work items are claimed from a global counter (algo 5) instead of dealt round-robin (algo 4) — see the producer.
+template <typename T, bool kClaim>
 __global__ void __launch_bounds__(kThreads, 1)
 own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorMap tm_plan, const __grid_constant__ CUtensorMap tm_g,
                const int2* __restrict__ tile_list, const int* __restrict__ pair_k, int* __restrict__ work_counter,
@@ -458,6 +459,7 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
     // ahead as the ring allows.
     const int rows_per_roi = C / kCS * Cfg<T>::kGBoxRows;
     unsigned s = 0, phase = 0, q = 0;
+    if constexpr (kClaim) {
     // Work items are CLAIMED, not dealt: the first one is blockIdx.x, the following ones come from a global counter in index
     // order (coarse levels first).  A CTA that starts late — its SM was still busy with another stream's kernel, e.g. an NCCL
     // all-reduce overlapping this backward — or that drew heavier items simply takes fewer of them.  Three claims are in
@@ -510,6 +512,48 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
       it0 = it1; lc0 = lc1; kk0 = kk1;
       it1 = it2; lc1 = lc2;
     }
+    } else {
+    int n_claimed = 0;
+    auto claim = [&]() -> int {
+      const int it = (int)blockIdx.x + n_claimed * (int)gridDim.x;
+      ++n_claimed;
+      return it < n_items ? it : -1;
+    };
+    int it = claim();
+    int2 lc = make_int2(0, 0);
+    int kk = 0;
+    if (it >= 0) {
+      lc = __ldg(tile_list + it / tg.n_slices);
+      kk = lane < lc.y ? __ldg(pair_k + lc.x + lane) : 0;
+    }
+    while (it >= 0) {
+      const int sl = it % tg.n_slices;
+      const int it_next = claim();
+      int2 lc_next = make_int2(0, 0);
+      int kk_next = 0;
+      if (it_next >= 0) {
+        lc_next = __ldg(tile_list + it_next / tg.n_slices);
+        kk_next = lane < lc_next.y ? __ldg(pair_k + lc_next.x + lane) : 0;
+      }
+      for (int p0 = 0; p0 < lc.y; p0 += 32) {
+        if (p0) kk = p0 + lane < lc.y ? __ldg(pair_k + lc.x + p0 + lane) : 0;
+        const int n = min(32, lc.y - p0);
+        for (int i = 0; i < n; ++i, ++q) {
+          const int k = __shfl_sync(0xffffffffu, kk, i);
+          if (lane == 0) {
+            unsigned char* st = smem + (size_t)s * SB;
+            if (q >= (unsigned)NS) mbar_wait_s(rs_s + kEmptyOff + s * 8u, phase ^ 1u);
+            mbar_expect_tx_s(rs_s + kFullOff + s * 8u, (unsigned)SB);
+            tmap_load_2d(st, &tm_plan, 0, k * Cfg<T>::kPlanBoxRows, &full[s]);
+            tmap_load_2d(st + sizeof(Plan), &tm_g, 0, k * rows_per_roi + sl * Cfg<T>::kGBoxRows, &full[s]);
+          }
+          if (++s == (unsigned)NS) { s = 0; phase ^= 1u; }
+        }
+        __syncwarp();
+      }
+      it = it_next; lc = lc_next; kk = kk_next;
+    }
+    }
     return;
   }
 
@@ -517,15 +561,26 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
     // ------------------------------------------------------------------ decoder: once per pair, intersects the RoI's live
     // rows / columns with the tile and publishes the result in info[stage]
     unsigned s = 0, phase = 0;
+    int2 lc_next = make_int2(0, 0);
+    if constexpr (!kClaim) lc_next = (int)blockIdx.x < n_items ? __ldg(tile_list + blockIdx.x / tg.n_slices) : make_int2(0, 0);
     for (unsigned n_it = 0;; ++n_it) {
-      const unsigned jr = n_it % kItemRing;
-      mbar_wait_s(rs_s + kItemFullOff + jr * 8u, (n_it / kItemRing) & 1u);
-      const uint4 e = lds_u4(rs_s + kItemOff + jr * 16u);
-      __syncwarp();
-      if (lane == 0) mbar_arrive_s(rs_s + kItemEmptyOff + jr * 8u);
-      if ((int)e.x < 0) break;
-      const int it = (int)e.x;
-      const int2 lc = make_int2((int)e.y, (int)e.z);
+      int it;
+      int2 lc;
+      if constexpr (kClaim) {
+        const unsigned jr = n_it % kItemRing;
+        mbar_wait_s(rs_s + kItemFullOff + jr * 8u, (n_it / kItemRing) & 1u);
+        const uint4 e = lds_u4(rs_s + kItemOff + jr * 16u);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_s(rs_s + kItemEmptyOff + jr * 8u);
+        if ((int)e.x < 0) break;
+        it = (int)e.x;
+        lc = make_int2((int)e.y, (int)e.z);
+      } else {
+        it = (int)blockIdx.x + (int)n_it * (int)gridDim.x;
+        if (it >= n_items) break;
+        lc = lc_next;
+        if (it + (int)gridDim.x < n_items) lc_next = __ldg(tile_list + (it + gridDim.x) / tg.n_slices);   // next item's list, early
+      }
       const TileAt a = tile_at(tg, it / tg.n_slices);
       for (int p = 0; p < lc.y; ++p) {
         mbar_wait_s(rs_s + kFullOff + s * 8u, phase);
@@ -605,15 +660,26 @@ own_bwd_kernel(const RoiDev g, const Tiles tg, const __grid_constant__ CUtensorM
   long long t_wait = 0, t_store = 0;
 #endif
   unsigned s = 0, phase = 0;                                // ring position of pair q
+  int2 lc_next = make_int2(0, 0);
+  if constexpr (!kClaim) lc_next = (int)blockIdx.x < n_items ? __ldg(tile_list + blockIdx.x / tg.n_slices) : make_int2(0, 0);
   for (unsigned n_it = 0;; ++n_it) {
-    const unsigned jr = n_it % kItemRing;
-    mbar_wait_s(rs_s + kItemFullOff + jr * 8u, (n_it / kItemRing) & 1u);
-    const uint4 e = lds_u4(rs_s + kItemOff + jr * 16u);
-    __syncwarp();
-    if (lane == 0) mbar_arrive_s(rs_s + kItemEmptyOff + jr * 8u);
-    if ((int)e.x < 0) break;
-    const int it = (int)e.x;
-    const int2 lc = make_int2((int)e.y, (int)e.z);
+    int it;
+    int2 lc;
+    if constexpr (kClaim) {
+      const unsigned jr = n_it % kItemRing;
+      mbar_wait_s(rs_s + kItemFullOff + jr * 8u, (n_it / kItemRing) & 1u);
+      const uint4 e = lds_u4(rs_s + kItemOff + jr * 16u);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_s(rs_s + kItemEmptyOff + jr * 8u);
+      if ((int)e.x < 0) break;
+      it = (int)e.x;
+      lc = make_int2((int)e.y, (int)e.z);
+    } else {
+      it = (int)blockIdx.x + (int)n_it * (int)gridDim.x;
+      if (it >= n_items) break;
+      lc = lc_next;
+      if (it + (int)gridDim.x < n_items) lc_next = __ldg(tile_list + (it + gridDim.x) / tg.n_slices);   // next item's list, early
+    }
     const int t_id = it / tg.n_slices, sl = it - t_id * tg.n_slices;
     const TileAt a = tile_at(tg, t_id);
     float2 acc[kRPW][kTileW];
@@ -818,7 +884,7 @@ size_t msroi_own_workspace(const RoiDev& g, int n_rois) {
   return own_layout(own_tiles(g), n_rois).total;
 }
 
-template <typename T>
+template <typename T, bool kClaim>
 static int launch_own(const RoiDev& g, const own::Tiles& tg, const OwnLayout& L, const void* grad_out, const float* rois,
                       int n_rois, const int32_t* roi_img_offsets, char* ws, cudaStream_t st) {
   static bool init = false;
@@ -827,7 +893,7 @@ static int launch_own(const RoiDev& g, const own::Tiles& tg, const OwnLayout& L,
     int dev = 0;
     DGOD_CUDA(cudaGetDevice(&dev));
     DGOD_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    DGOD_CUDA(cudaFuncSetAttribute(own::own_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, own::Cfg<T>::kSmem));
+    DGOD_CUDA(cudaFuncSetAttribute(own::own_bwd_kernel<T, kClaim>, cudaFuncAttributeMaxDynamicSharedMemorySize, own::Cfg<T>::kSmem));
     init = true;
   }
   int* cursor = reinterpret_cast<int*>(ws);
@@ -859,14 +925,14 @@ static int launch_own(const RoiDev& g, const own::Tiles& tg, const OwnLayout& L,
                          CF::kGBoxRows);
     if (rc) return rc;
   }
-  own::own_bwd_kernel<T><<<grid, own::kThreads, own::Cfg<T>::kSmem, st>>>(g, tg, tm_plan, tm_g, tile_list, pair_k, cursor + 4,
+  own::own_bwd_kernel<T, kClaim><<<grid, own::kThreads, own::Cfg<T>::kSmem, st>>>(g, tg, tm_plan, tm_g, tile_list, pair_k, cursor + 4,
                                                                        reinterpret_cast<long long*>(ws + 1024));
   DGOD_LAUNCHED();
   return DGOD_OK;
 }
 
 int msroi_bwd_own(const dgod_roi_config* cfg, const RoiDev& g, const void* grad_out, const float* rois, int n_rois,
-                  const int32_t* roi_img_offsets, void* workspace, size_t workspace_bytes, cudaStream_t st, int* handled) {
+                  const int32_t* roi_img_offsets, void* workspace, size_t workspace_bytes, cudaStream_t st, int* handled, int claim) {
   *handled = 0;
   if (!own_shape_ok(g) || ((uintptr_t)grad_out & 15)) return DGOD_OK;
   if (!workspace || ((uintptr_t)workspace & 127)) return DGOD_OK;
@@ -875,8 +941,12 @@ int msroi_bwd_own(const dgod_roi_config* cfg, const RoiDev& g, const void* grad_
   const OwnLayout L = own_layout(tg, n_rois);
   if (workspace_bytes < L.total) return DGOD_OK;
   *handled = 1;
-  return cfg->dtype == DGOD_F32 ? launch_own<float>(g, tg, L, grad_out, rois, n_rois, roi_img_offsets, (char*)workspace, st)
-                                : launch_own<__nv_bfloat16>(g, tg, L, grad_out, rois, n_rois, roi_img_offsets, (char*)workspace, st);
+  char* ws = (char*)workspace;
+  if (cfg->dtype == DGOD_F32)
+    return claim ? launch_own<float, true>(g, tg, L, grad_out, rois, n_rois, roi_img_offsets, ws, st)
+                 : launch_own<float, false>(g, tg, L, grad_out, rois, n_rois, roi_img_offsets, ws, st);
+  return claim ? launch_own<__nv_bfloat16, true>(g, tg, L, grad_out, rois, n_rois, roi_img_offsets, ws, st)
+               : launch_own<__nv_bfloat16, false>(g, tg, L, grad_out, rois, n_rois, roi_img_offsets, ws, st);
 }
 
 }  // namespace dgod

@@ -690,7 +690,7 @@ def _msroi_bwd_op(grad: Tensor, rois: Tensor, roi_img_offsets: Optional[Tensor],
     lib = _lib.load()
     n_levels = len(scales)
     b, c = shapes[0], shapes[1]
-    if not channels_last and not aligned and algo in (0, 3, 4) and _tma_shape(c, pooled_h, pooled_w, sampling_ratio):
+    if not channels_last and not aligned and algo in (0, 3, 4, 5) and _tma_shape(c, pooled_h, pooled_w, sampling_ratio):
         channels_last = True     # gradients of NCHW maps are returned in channels_last memory (same values)
     mf = torch.channels_last if channels_last else torch.contiguous_format
     grads = [torch.empty((b, c, shapes[2 + 2 * l], shapes[3 + 2 * l]), dtype=grad.dtype, device=grad.device,
@@ -721,7 +721,10 @@ def _(grad, rois, roi_img_offsets, shapes, channels_last, scales, pooled_h, pool
 
 import os as _os
 
-BACKWARD_ALGO = int(_os.environ.get("DGOD_BWD_ALGO", "0"))  # 0 auto, 1 atomic / vector-RED scatter, 2 tile gather
+# 0 auto (= 4 where the shape allows), 1 atomic / vector-RED scatter, 2 tile gather, 3 bulk-reduce scatter, 4 owner-computes with
+# a static deal of the work items, 5 owner-computes with claimed work items: what ddp.GradSync selects when gradients are
+# all-reduced during backward (NCCL kernels then hold SMs when the persistent backward kernel starts)
+BACKWARD_ALGO = int(_os.environ.get("DGOD_BWD_ALGO", "0"))
 
 
 def _msroi_setup(ctx, inputs, output):

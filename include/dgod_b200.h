@@ -267,7 +267,7 @@ int dgod_msroi_align_bwd(const dgod_roi_config* cfg /*host*/,
                          const float* rois, int n_rois,
                          const int32_t* roi_img_offsets /*device [batch+1] or NULL*/,
                          void* const* grad_feats /*host array of device ptrs*/,
-                         int algo /*0 auto, 1 scatter, 2 tile gather, 3 TMA bulk reduce, 4 owner-computes*/,
+                         int algo /*0 auto, 1 scatter, 2 tile gather, 3 TMA bulk reduce, 4 owner-computes, 5 owner-computes with claimed work items*/,
                          void* workspace, size_t workspace_bytes, dgod_stream_t stream);
 
 /* ------------------------------------------------------------------ box head post-processing */

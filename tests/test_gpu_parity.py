@@ -258,8 +258,8 @@ def test_multiscale_roi_align(dtype, tol, nhwc):
         go = go.to(dtype).float()
     grads = O.msroi_align_bwd(go.numpy(), [tuple(f.shape) for f in feats], rois.numpy(), scales, 2, 2, 5)
     from dgod_b200 import ops
-    # atomic scatter / tile gather / TMA bulk reduce (channels_last only) / auto
-    algos = ((1, 2) if dtype == torch.float32 else (2,)) + ((3,) if nhwc else ()) + (0,)
+    # atomic scatter / tile gather / TMA bulk reduce, owner-computes with dealt and with claimed work items (channels_last only) / auto
+    algos = ((1, 2) if dtype == torch.float32 else (2,)) + ((3, 4, 5) if nhwc else ()) + (0,)
     for algo in algos:
         ops.BACKWARD_ALGO = algo
         try:
