@@ -20,9 +20,11 @@
 //                    bin such that all its weights sit on 4 consecutive bins (3 of 4 RoIs have one) ->
 //                    a 2 560-byte plan; plus a 16-byte record (level, image, footprint box).
 //   own_bin_kernel   one warp per tile: the RoIs (index order) whose footprint box meets the tile.
-//   own_bwd_kernel   persistent, one CTA per SM, 16 warps, work items (tile x 64-channel slice) claimed from a
-//                    global counter, coarse levels first (a CTA whose SM was still held by another stream's
-//                    kernel — an NCCL all-reduce overlapping backward — just takes fewer).  Warp roles:
+//   own_bwd_kernel   persistent, one CTA per SM, 16 warps, work items (tile x 64-channel slice), coarse levels first:
+//                    dealt round-robin (algo 4, the default: best L2 locality, 267 us in a single-GPU step) or claimed
+//                    from a global counter (algo 5, kClaim: a CTA whose SM is still held by another stream's kernel —
+//                    an NCCL all-reduce overlapping backward — just takes fewer items: 277 vs 342 us in a 2-GPU step,
+//                    291 us in a single-GPU one).  Warp roles:
 //                      producer  lane 0 streams (plan, [64][49] gradient slice) pairs through a ring of 15
 //                                stages with two tensor-map loads per stage (cp.async.bulk.tensor, SASS
 //                                UTMALDG; completion counted in bytes on the stage's `full` mbarrier);
