@@ -26,6 +26,8 @@ bitonic_local_kernel(unsigned long long* __restrict__ keys, uint32_t* __restrict
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* sk = reinterpret_cast<unsigned long long*>(smem_raw);
   uint32_t* sv = reinterpret_cast<uint32_t*>(sk + tile);
+  pdl_wait();                          // the steps of the network are launched behind one another (programmatic dependent launch)
+  pdl_trigger();
   const long long base = (long long)blockIdx.x * tile;
   for (int i = threadIdx.x; i < tile; i += blockDim.x) {
     sk[i] = keys[base + i];
@@ -62,6 +64,8 @@ bitonic_local_kernel(unsigned long long* __restrict__ keys, uint32_t* __restrict
 __global__ void __launch_bounds__(256)
 bitonic_global_kernel(unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals,
                       int n_pow2, int k, int j) {
+  pdl_wait();
+  pdl_trigger();
   long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= (n_pow2 >> 1)) return;
   long long i = 2 * q - (q & (long long)(j - 1));
@@ -95,14 +99,14 @@ static inline int bitonic_sort(unsigned long long* keys, uint32_t* vals, int n_p
   const int threads = tile / 2 < kSortThreads ? (tile / 2 < 32 ? 32 : tile / 2) : kSortThreads;
   const size_t smem = (size_t)tile * 12;
   const int n_tiles = n_pow2 / tile;
-  bitonic_local_kernel<<<n_tiles, threads, smem, st>>>(keys, vals, n_pow2, tile, 0, 0);
+  DGOD_CUDA(launch_pdl(bitonic_local_kernel, dim3(n_tiles), dim3(threads), smem, st, keys, vals, n_pow2, tile, 0, 0));
   DGOD_LAUNCHED();
   for (long long k = (long long)tile * 2; k <= n_pow2; k <<= 1) {
     for (long long j = k >> 1; j >= tile; j >>= 1) {
-      bitonic_global_kernel<<<cdiv(n_pow2 / 2, 256), 256, 0, st>>>(keys, vals, n_pow2, (int)k, (int)j);
+      DGOD_CUDA(launch_pdl(bitonic_global_kernel, dim3(cdiv(n_pow2 / 2, 256)), dim3(256), 0, st, keys, vals, n_pow2, (int)k, (int)j));
       DGOD_LAUNCHED();
     }
-    bitonic_local_kernel<<<n_tiles, threads, smem, st>>>(keys, vals, n_pow2, tile, 1, (int)k);
+    DGOD_CUDA(launch_pdl(bitonic_local_kernel, dim3(n_tiles), dim3(threads), smem, st, keys, vals, n_pow2, tile, 1, (int)k));
     DGOD_LAUNCHED();
   }
   return DGOD_OK;
