@@ -220,7 +220,7 @@ class B200Run:
         self.sync = None
         if world > 1:
             from dgod_b200.ddp import GradSync
-            self.sync = GradSync(list(model.parameters()), world)
+            self.sync = GradSync(list(model.parameters()), world, bucket_bytes=int(os.environ.get("DGOD_BUCKET_MB", "32")) << 20)
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.modes = cycle_modes(exp)
         torch.cuda.synchronize()
