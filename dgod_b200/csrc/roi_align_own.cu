@@ -41,8 +41,9 @@
 //
 // Roofline: HBM.  Algorithmic bytes K*C*49*s + 20K + sum_l B*C*H_l*W_l*s; measured DRAM
 // traffic 0.98x of that (profiles/).  On chip the gradient slices are re-read once per tile an RoI meets
-// (2.8 at this tile size) from the L2.  What bounds the kernel today is instruction issue in the consumer
-// warps (profiles/README.md has the ablation: ring + decode 40 %, T 10 %, block sweeps 35 %, stores 15 %).
+// (2.8 at this tile size) from the L2.  What bounds the kernel today is instruction issue at low warp-level parallelism
+// (16 warps x 128 registers per SM; profiles/README.md has the ablation — of 293 us: T phase 37, block sweeps 101, stores
+// 28, ring + decode + loop skeleton 157 — the ncu stall profile and the variants that were measured and not kept).
 // Compile-time switches for those ablations: DGOD_OWN_SKIP_T / _SKIP_COLS / _SKIP_STORE, DGOD_OWN_TIMING.
 #include <algorithm>
 #include "roi_common.cuh"
